@@ -1,0 +1,651 @@
+/*
+ * fmb_api.cu -- host side of the C ABI declared in include/fmb.h.
+ *
+ * Owns device memory, CUDA streams/events and the per-step bookkeeping that the
+ * reference keeps inside struct demod_state (resampler phase prev_lpr_index,
+ * rtl_fm_player.h:169) and demod_thread_fn (src/rtl_fm_player.c:855-933).
+ * No CPU fallback: every compute entry point launches the CUDA kernels or fails.
+ */
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fmb_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long> g_launches{0};
+
+int set_err(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess)
+        snprintf(g_err, sizeof g_err, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(g_err, sizeof g_err, "%s", what);
+    return code;
+}
+
+#define CU(call)                                                               \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) return set_err(FMB_ERR_CUDA, #call, e_);        \
+    } while (0)
+
+constexpr int kProfMax = 4096; /* event pairs kept per kernel between profile resets */
+
+struct Slot { /* one in-flight block-step of the pipelined host path */
+    uint8_t *d_iq = nullptr;
+    int16_t *d_pcm = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_iq_free = nullptr, ev_done = nullptr;
+    int n_out = 0;
+    bool busy = false;
+};
+
+} // namespace
+
+struct fmb_handle {
+    fmb_config cfg;
+    fmb_tables tab;
+    int n_dem;                 /* demodulated samples per stream per step */
+    int segs, seg_len;
+    int max_out;
+    /* resampler bookkeeping (common to all streams) */
+    int phase;                 /* prev_lpr_index */
+    uint64_t blocks_done;
+    /* device memory */
+    fmb_stream_state *d_state[2] = {nullptr, nullptr};
+    int state_cur = 0;
+    float *d_de_state = nullptr;     /* [n_streams][2] */
+    float *d_lr[2] = {nullptr, nullptr};
+    long long lr_pitch = 0;
+    int lr_cur = 0;
+    float *d_dem = nullptr;          /* debug tap */
+    int debug = 0;
+    int last_n_out = 0, last_lr = 0;
+    /* streams / events */
+    cudaStream_t s_aux = nullptr, s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_demod[2] = {nullptr, nullptr}, ev_deemph[2] = {nullptr, nullptr};
+    bool deemph_pending[2] = {false, false};
+    cudaEvent_t ev_fork = nullptr;
+    /* pipelined host path */
+    Slot slot[FMB_PIPE_DEPTH];
+    size_t d_iq_pitch = 0, d_pcm_pitch = 0;
+    int next_ticket = 0;
+    /* profiling */
+    int profile = 0;
+    cudaEvent_t *pev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; /* [kernel][start/stop][i] */
+    int pcount[2] = {0, 0};
+    double pms[2] = {0, 0};
+    int plaunch[2] = {0, 0};
+};
+
+namespace {
+
+/* int16 values the step starting at resampler phase `phase` produces */
+int out_count_for(const fmb_handle *h, int phase)
+{
+    const fmb_config &c = h->cfg;
+    if (c.rate_out2 <= 0) return h->n_dem;
+    const long long ticks = ((long long) phase + (long long) h->n_dem * c.rate_out2) / c.rate_in;
+    return (int) (c.mode == 2 ? 2 * ticks : ticks);
+}
+
+int next_phase(const fmb_handle *h, int phase)
+{
+    const fmb_config &c = h->cfg;
+    if (c.rate_out2 <= 0) return phase;
+    return (int) (((long long) phase + (long long) h->n_dem * c.rate_out2) % c.rate_in);
+}
+
+/* Does the reference's in-place output overwrite (src/rtl_fm_player.c:593-597)
+ * hit an input that is still to be read, anywhere but the handled case
+ * "tick on sample 0 clobbers sample 1"?  Simulates one block's index walk. */
+bool unhandled_inplace_hazard(const fmb_handle *h, int phase)
+{
+    const fmb_config &c = h->cfg;
+    if (c.mode != 2 || c.rate_out2 <= 0) return false;
+    long long p = phase;
+    int o = 0;
+    for (int i = 0; i < h->n_dem; ++i) {
+        p += c.rate_out2;
+        if (p >= c.rate_in) {
+            p -= c.rate_in;
+            /* writes ib[o], ib[o+1] after reading ib[i] */
+            if (o + 1 > i && !(i == 0)) return true;
+            o += 2;
+        }
+    }
+    return false;
+}
+
+bool tick_on_first_sample(const fmb_handle *h, int phase)
+{
+    const fmb_config &c = h->cfg;
+    return c.mode == 2 && c.rate_out2 > 0 && (long long) phase + c.rate_out2 >= c.rate_in;
+}
+
+int pick_segments(int n_streams, int n_dem)
+{
+    /* Fill 148 SMs x 2 resident CTAs; each extra segment costs FMB_WARM recomputed samples. */
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = 2 * sms;
+    const int max_segs = n_dem / FMB_NSUB;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= max_segs && s <= 8; s *= 2) {
+        if ((n_dem / FMB_NSUB) % s) continue;
+        const double ctas = (double) n_streams * s;
+        const double waves = (double) ((long long) ((ctas + slots - 1) / slots));
+        const double per_cta = (double) n_dem / s + (s > 1 ? FMB_WARM * 2.0 : 0.0);
+        const double cost = waves * per_cta;
+        if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+void destroy_events(cudaEvent_t *ev, int n)
+{
+    if (!ev) return;
+    for (int i = 0; i < n; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    free(ev);
+}
+
+int ensure_profile_events(fmb_handle *h)
+{
+    for (int k = 0; k < 2; ++k)
+        for (int e = 0; e < 2; ++e)
+            if (!h->pev[k][e]) {
+                h->pev[k][e] = (cudaEvent_t *) calloc(kProfMax, sizeof(cudaEvent_t));
+                if (!h->pev[k][e]) return set_err(FMB_ERR_NOMEM, "profile events");
+                for (int i = 0; i < kProfMax; ++i) CU(cudaEventCreate(&h->pev[k][e][i]));
+            }
+    return FMB_OK;
+}
+
+int fold_profile(fmb_handle *h)
+{
+    for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < h->pcount[k]; ++i) {
+            float ms = 0.f;
+            CU(cudaEventSynchronize(h->pev[k][1][i]));
+            CU(cudaEventElapsedTime(&ms, h->pev[k][0][i], h->pev[k][1][i]));
+            h->pms[k] += ms;
+            h->plaunch[k] += 1;
+        }
+        h->pcount[k] = 0;
+    }
+    return FMB_OK;
+}
+
+/* Enqueue one block-step: demod kernel on `sm`, de-emphasis kernel on the aux
+ * stream.  d_iq/d_pcm are device pointers. */
+int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d_pcm, size_t pcm_pitch,
+                 cudaStream_t sm, int *n_out_ret)
+{
+    const fmb_config &c = h->cfg;
+    const int n_out = out_count_for(h, h->phase);
+    if ((size_t) n_out > pcm_pitch) return set_err(FMB_ERR_ARG, "pcm_pitch smaller than fmb_next_out_count()");
+    if (iq_pitch < (size_t) c.block_bytes || (iq_pitch & 15) || ((uintptr_t) d_iq & 15))
+        return set_err(FMB_ERR_ARG, "iq pointer/pitch must be 16-byte aligned and pitch >= block_bytes");
+    const bool quirk = c.emulate_inplace_quirk && tick_on_first_sample(h, h->phase);
+    if (c.emulate_inplace_quirk && unhandled_inplace_hazard(h, h->phase))
+        return set_err(FMB_ERR_UNSUPPORTED,
+                       "rate_in/rate_out2 ratio makes the reference's in-place stereo output overwrite unread input "
+                       "beyond the emulated first-sample case");
+
+    const int b = h->lr_cur;
+    /* the de-emphasis pass that last read d_lr[b] must be done before we overwrite it */
+    if (h->deemph_pending[b]) CU(cudaStreamWaitEvent(sm, h->ev_deemph[b], 0));
+
+    fmb_kparams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.iq = d_iq;
+    kp.iq_pitch = (long long) iq_pitch;
+    kp.st_in = h->d_state[h->state_cur];
+    kp.st_out = h->d_state[h->state_cur ^ 1];
+    kp.lr = h->d_lr[b];
+    kp.lr_pitch = h->lr_pitch;
+    kp.dem_dump = h->debug ? h->d_dem : nullptr;
+    kp.dem_pitch = h->n_dem;
+    kp.n_streams = c.n_streams;
+    kp.segs = h->segs;
+    kp.seg_len = h->seg_len;
+    kp.n_dem = h->n_dem;
+    if (c.rate_out2 > 0) {
+        kp.slow = c.rate_out2; kp.fast = c.rate_in; kp.phase0 = h->phase;
+        if (c.rate_in % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0) {
+            kp.dec = c.rate_in / c.rate_out2;
+            kp.dec_c0 = h->phase / c.rate_out2;
+        }
+    } else { /* lp_real_f32 skipped: every sample is an output */
+        kp.slow = 1; kp.fast = 1; kp.phase0 = 0; kp.dec = 1; kp.dec_c0 = 0;
+    }
+    kp.quirk = quirk ? 1 : 0;
+
+    fmb_config kc = c;
+    if (c.rate_out2 <= 0) kc.mode = 0;
+
+    const bool prof = h->profile && h->pcount[0] < kProfMax && h->pcount[1] < kProfMax;
+    if (prof) CU(cudaEventRecord(h->pev[0][0][h->pcount[0]], sm));
+    cudaError_t e = (cudaError_t) fmb_launch_demod(&kc, &kp, &h->tab, sm);
+    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_demod_kernel launch", e);
+    g_launches++;
+    if (prof) { CU(cudaEventRecord(h->pev[0][1][h->pcount[0]], sm)); h->pcount[0]++; }
+    CU(cudaEventRecord(h->ev_demod[b], sm));
+
+    /* de-emphasis + int16 on the aux stream, in step order */
+    CU(cudaStreamWaitEvent(h->s_aux, h->ev_demod[b], 0));
+    fmb_dparams dp;
+    memset(&dp, 0, sizeof dp);
+    dp.lr = h->d_lr[b];
+    dp.lr_pitch = h->lr_pitch;
+    dp.pcm = d_pcm;
+    dp.pcm_pitch = (long long) pcm_pitch;
+    dp.de_state = h->d_de_state;
+    dp.n_streams = c.n_streams;
+    dp.n_out = n_out;
+    dp.pairs = c.mode == 2;
+    dp.do_deemph = c.deemph != 0.0;
+    dp.lambda = h->tab.lambda;
+    dp.pcm_scale = h->tab.pcm_scale;
+    if (prof) CU(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
+    e = (cudaError_t) fmb_launch_deemph(&dp, h->s_aux);
+    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_deemph_kernel launch", e);
+    g_launches++;
+    if (prof) { CU(cudaEventRecord(h->pev[1][1][h->pcount[1]], h->s_aux)); h->pcount[1]++; }
+    CU(cudaEventRecord(h->ev_deemph[b], h->s_aux));
+    h->deemph_pending[b] = true;
+
+    h->last_n_out = n_out;
+    h->last_lr = b;
+    h->lr_cur ^= 1;
+    h->state_cur ^= 1;
+    h->phase = next_phase(h, h->phase);
+    h->blocks_done++;
+    if (n_out_ret) *n_out_ret = n_out;
+    return FMB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *fmb_last_error(void) { return g_err; }
+long fmb_launch_count(void) { return g_launches.load(); }
+const char *fmb_version(void) { return "rtl_fm_player_b200 0.1 (sm_100a)"; }
+
+int fmb_default_config(fmb_config *cfg)
+{
+    if (!cfg) return set_err(FMB_ERR_ARG, "cfg is NULL");
+    memset(cfg, 0, sizeof *cfg);
+    cfg->rate_in = 240000;     /* DEFAULT_SAMPLE_RATE, rtl_fm_player.h:30, demod_init :1158 */
+    cfg->rate_out2 = 48000;    /* :1171 */
+    cfg->mode = 2;             /* :1183 */
+    cfg->size = 90;            /* :1184 */
+    cfg->offset_tuning = 0;    /* :1170 */
+    cfg->deemph = 0.000050;    /* DEEMPHASIS_FM_EU, h:45, :1169 */
+    cfg->volume = 0.4f;        /* :1181 */
+    cfg->n_streams = 1;
+    cfg->block_bytes = FMB_REF_BLOCK_BYTES;
+    cfg->device = 0;
+    cfg->precision = FMB_PRECISION_EXACT;
+    cfg->segments = 0;
+    cfg->emulate_inplace_quirk = 1;
+    return FMB_OK;
+}
+
+int fmb_preset_stereo_192k(fmb_config *cfg) /* -X, :1464-1476 */
+{
+    if (!cfg) return set_err(FMB_ERR_ARG, "cfg is NULL");
+    cfg->rate_in = 192000; cfg->rate_out2 = 48000; cfg->deemph = 0.000050; cfg->mode = 2; cfg->size = 90;
+    return FMB_OK;
+}
+
+int fmb_preset_mono_192k(fmb_config *cfg) /* -Y, :1477-1488 */
+{
+    if (!cfg) return set_err(FMB_ERR_ARG, "cfg is NULL");
+    cfg->rate_in = 192000; cfg->rate_out2 = 48000; cfg->deemph = 0.000050; cfg->mode = 1; cfg->size = 128;
+    return FMB_OK;
+}
+
+int fmb_create(const fmb_config *cfg, fmb_handle **out)
+{
+    if (!cfg || !out) return set_err(FMB_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (cfg->n_streams < 1 || cfg->rate_in <= 0 || cfg->mode < 0 || cfg->mode > 2)
+        return set_err(FMB_ERR_ARG, "bad n_streams / rate_in / mode");
+    if (cfg->block_bytes < FMB_BLOCK_QUANTUM || cfg->block_bytes % FMB_BLOCK_QUANTUM)
+        return set_err(FMB_ERR_ARG, "block_bytes must be a positive multiple of 32768");
+    if (cfg->precision != FMB_PRECISION_EXACT && cfg->precision != FMB_PRECISION_FMA)
+        return set_err(FMB_ERR_ARG, "bad precision");
+    if (cfg->rate_out2 > cfg->rate_in) return set_err(FMB_ERR_UNSUPPORTED, "rate_out2 > rate_in");
+    if (cfg->mode == 2 && cfg->rate_out2 > 0 && 2LL * cfg->rate_out2 > cfg->rate_in)
+        return set_err(FMB_ERR_UNSUPPORTED, "stereo needs rate_in >= 2*rate_out2 (in-place output, reference :593-597)");
+    {
+        const int kmode = cfg->rate_out2 > 0 ? cfg->mode : 0;
+        if (fmb_demod_supported(kmode, cfg->size) != 0)
+            return set_err(FMB_ERR_UNSUPPORTED, "no kernel compiled for this lpr.mode / lpr.size (have mode 1,2 x size 90,128; mode 0)");
+    }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(FMB_ERR_CUDA, "no CUDA device (this library has no CPU fallback)", e);
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err(FMB_ERR_ARG, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+
+    fmb_handle *h = new (std::nothrow) fmb_handle();
+    if (!h) return set_err(FMB_ERR_NOMEM, "handle");
+    h->cfg = *cfg;
+    int rc = fmb_design_tables(cfg, &h->tab);
+    if (rc != FMB_OK) { delete h; return set_err(rc, "filter design rejected the configuration"); }
+    h->n_dem = cfg->block_bytes / 16;
+    h->segs = cfg->segments > 0 ? cfg->segments : pick_segments(cfg->n_streams, h->n_dem);
+    if (h->segs < 1 || (h->n_dem / FMB_NSUB) % h->segs || h->segs > h->n_dem / FMB_NSUB) {
+        delete h;
+        return set_err(FMB_ERR_ARG, "segments must divide block_bytes/32768");
+    }
+    h->seg_len = h->n_dem / h->segs;
+    h->cfg.segments = h->segs;
+    h->phase = 0;
+    h->blocks_done = 0;
+    /* upper bound of outputs per step */
+    if (cfg->rate_out2 > 0) {
+        const long long t = ((long long) cfg->rate_in - 1 + (long long) h->n_dem * cfg->rate_out2) / cfg->rate_in;
+        h->max_out = (int) (cfg->mode == 2 ? 2 * t : t);
+    } else {
+        h->max_out = h->n_dem;
+    }
+    h->lr_pitch = ((long long) h->max_out + 7) & ~7LL;
+
+    const size_t st_bytes = sizeof(fmb_stream_state) * (size_t) cfg->n_streams;
+#define CUH(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { set_err(FMB_ERR_CUDA, #call, e_); fmb_destroy(h); return FMB_ERR_CUDA; } \
+    } while (0)
+    for (int i = 0; i < 2; ++i) {
+        CUH(cudaMalloc(&h->d_state[i], st_bytes));
+        CUH(cudaMemset(h->d_state[i], 0, st_bytes));
+        CUH(cudaMalloc(&h->d_lr[i], (size_t) h->lr_pitch * cfg->n_streams * sizeof(float)));
+        CUH(cudaMemset(h->d_lr[i], 0, (size_t) h->lr_pitch * cfg->n_streams * sizeof(float)));
+        CUH(cudaEventCreateWithFlags(&h->ev_demod[i], cudaEventDisableTiming));
+        CUH(cudaEventCreateWithFlags(&h->ev_deemph[i], cudaEventDisableTiming));
+    }
+    CUH(cudaMalloc(&h->d_de_state, sizeof(float) * 2 * (size_t) cfg->n_streams));
+    CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
+    CUH(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+    CUH(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    CUH(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CUH(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUH(cudaDeviceSynchronize());
+#undef CUH
+    *out = h;
+    return FMB_OK;
+}
+
+int fmb_destroy(fmb_handle *h)
+{
+    if (!h) return FMB_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_state[i]) cudaFree(h->d_state[i]);
+        if (h->d_lr[i]) cudaFree(h->d_lr[i]);
+        if (h->ev_demod[i]) cudaEventDestroy(h->ev_demod[i]);
+        if (h->ev_deemph[i]) cudaEventDestroy(h->ev_deemph[i]);
+    }
+    if (h->d_de_state) cudaFree(h->d_de_state);
+    if (h->d_dem) cudaFree(h->d_dem);
+    for (auto &s : h->slot) {
+        if (s.d_iq) cudaFree(s.d_iq);
+        if (s.d_pcm) cudaFree(s.d_pcm);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_iq_free) cudaEventDestroy(s.ev_iq_free);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int k = 0; k < 2; ++k)
+        for (int e = 0; e < 2; ++e) destroy_events(h->pev[k][e], kProfMax);
+    delete h;
+    return FMB_OK;
+}
+
+int fmb_reset(fmb_handle *h)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const size_t st_bytes = sizeof(fmb_stream_state) * (size_t) h->cfg.n_streams;
+    for (int i = 0; i < 2; ++i) CU(cudaMemset(h->d_state[i], 0, st_bytes));
+    CU(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) h->cfg.n_streams));
+    h->phase = 0;
+    h->blocks_done = 0;
+    h->deemph_pending[0] = h->deemph_pending[1] = false;
+    for (auto &s : h->slot) s.busy = false;
+    return FMB_OK;
+}
+
+int fmb_next_out_count(const fmb_handle *h) { return h ? out_count_for(h, h->phase) : FMB_ERR_ARG; }
+int fmb_max_out_count(const fmb_handle *h) { return h ? h->max_out : FMB_ERR_ARG; }
+
+int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, int16_t *pcm_dev, size_t pcm_pitch,
+                       void *stream)
+{
+    if (!h || !iq_dev || !pcm_dev) return set_err(FMB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    return enqueue_step(h, iq_dev, iq_pitch, pcm_dev, pcm_pitch, (cudaStream_t) stream, nullptr);
+}
+
+int fmb_join(fmb_handle *h, void *stream)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    for (int b = 0; b < 2; ++b)
+        if (h->deemph_pending[b]) CU(cudaStreamWaitEvent((cudaStream_t) stream, h->ev_deemph[b], 0));
+    return FMB_OK;
+}
+
+static int ensure_slots(fmb_handle *h)
+{
+    if (h->slot[0].d_iq) return FMB_OK;
+    const fmb_config &c = h->cfg;
+    h->d_iq_pitch = (size_t) c.block_bytes;
+    h->d_pcm_pitch = ((size_t) h->max_out + 7) & ~(size_t) 7;
+    for (auto &s : h->slot) {
+        CU(cudaMalloc(&s.d_iq, h->d_iq_pitch * c.n_streams));
+        CU(cudaMalloc(&s.d_pcm, h->d_pcm_pitch * c.n_streams * sizeof(int16_t)));
+        CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_iq_free, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        s.busy = false;
+    }
+    return FMB_OK;
+}
+
+int fmb_submit(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t *pcm_host, size_t pcm_pitch, int *ticket)
+{
+    if (!h || !iq_host || !pcm_host) return set_err(FMB_ERR_ARG, "NULL argument");
+    const fmb_config &c = h->cfg;
+    if (iq_pitch < (size_t) c.block_bytes) return set_err(FMB_ERR_ARG, "iq_pitch < block_bytes");
+    CU(cudaSetDevice(c.device));
+    int rc = ensure_slots(h);
+    if (rc != FMB_OK) return rc;
+    const int t = h->next_ticket;
+    Slot &s = h->slot[t % FMB_PIPE_DEPTH];
+    if (s.busy) return set_err(FMB_ERR_STATE, "pipeline full: fmb_wait() the oldest ticket first");
+    const int n_out = out_count_for(h, h->phase);
+    if ((size_t) n_out > pcm_pitch) return set_err(FMB_ERR_ARG, "pcm_pitch smaller than fmb_next_out_count()");
+
+    /* H2D on its own stream; the slot's previous demod has been waited for by the host (busy == false) */
+    CU(cudaMemcpy2DAsync(s.d_iq, h->d_iq_pitch, iq_host, iq_pitch, (size_t) c.block_bytes, (size_t) c.n_streams,
+                         cudaMemcpyHostToDevice, h->s_h2d));
+    CU(cudaEventRecord(s.ev_h2d, h->s_h2d));
+    CU(cudaStreamWaitEvent(h->s_main, s.ev_h2d, 0));
+    rc = enqueue_step(h, s.d_iq, h->d_iq_pitch, s.d_pcm, h->d_pcm_pitch, h->s_main, &s.n_out);
+    if (rc != FMB_OK) return rc;
+    /* D2H after this step's de-emphasis */
+    CU(cudaStreamWaitEvent(h->s_d2h, h->ev_deemph[h->last_lr], 0));
+    if (s.n_out > 0)
+        CU(cudaMemcpy2DAsync(pcm_host, pcm_pitch * sizeof(int16_t), s.d_pcm, h->d_pcm_pitch * sizeof(int16_t),
+                             (size_t) s.n_out * sizeof(int16_t), (size_t) c.n_streams, cudaMemcpyDeviceToHost, h->s_d2h));
+    CU(cudaEventRecord(s.ev_done, h->s_d2h));
+    s.busy = true;
+    h->next_ticket++;
+    if (ticket) *ticket = t;
+    return FMB_OK;
+}
+
+int fmb_wait(fmb_handle *h, int ticket, int *n_out)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    if (ticket < 0 || ticket >= h->next_ticket || ticket < h->next_ticket - FMB_PIPE_DEPTH)
+        return set_err(FMB_ERR_STATE, "unknown or expired ticket");
+    Slot &s = h->slot[ticket % FMB_PIPE_DEPTH];
+    if (!s.busy) return set_err(FMB_ERR_STATE, "ticket already waited for");
+    CU(cudaEventSynchronize(s.ev_done));
+    s.busy = false;
+    if (n_out)
+        for (int i = 0; i < h->cfg.n_streams; ++i) n_out[i] = s.n_out;
+    return FMB_OK;
+}
+
+int fmb_process(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t *pcm_host, size_t pcm_pitch, int *n_out)
+{
+    int ticket = -1;
+    int rc = fmb_submit(h, iq_host, iq_pitch, pcm_host, pcm_pitch, &ticket);
+    if (rc != FMB_OK) return rc;
+    return fmb_wait(h, ticket, n_out);
+}
+
+int fmb_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return set_err(FMB_ERR_ARG, "NULL argument");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return FMB_OK;
+}
+
+int fmb_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return FMB_OK;
+}
+
+int fmb_get_state(fmb_handle *h, int first, int count, fmb_stream_state *out, int *prev_lpr_index, uint64_t *blocks_done)
+{
+    if (!h || !out || first < 0 || count < 0 || first + count > h->cfg.n_streams)
+        return set_err(FMB_ERR_ARG, "bad state range");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, h->d_state[h->state_cur] + first, sizeof(fmb_stream_state) * (size_t) count, cudaMemcpyDeviceToHost));
+    float *de = (float *) malloc(sizeof(float) * 2 * (size_t) (count ? count : 1));
+    if (!de) return set_err(FMB_ERR_NOMEM, "state");
+    cudaError_t e = cudaMemcpy(de, h->d_de_state + 2 * first, sizeof(float) * 2 * (size_t) count, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(de); return set_err(FMB_ERR_CUDA, "cudaMemcpy de_state", e); }
+    for (int i = 0; i < count; ++i) { out[i].deemph_l = de[2 * i]; out[i].deemph_r = de[2 * i + 1]; }
+    free(de);
+    if (prev_lpr_index) *prev_lpr_index = h->phase;
+    if (blocks_done) *blocks_done = h->blocks_done;
+    return FMB_OK;
+}
+
+int fmb_set_state(fmb_handle *h, int first, int count, const fmb_stream_state *in, int prev_lpr_index, uint64_t blocks_done)
+{
+    if (!h || !in || first < 0 || count < 0 || first + count > h->cfg.n_streams)
+        return set_err(FMB_ERR_ARG, "bad state range");
+    if (prev_lpr_index < 0 || prev_lpr_index >= h->cfg.rate_in) return set_err(FMB_ERR_ARG, "bad prev_lpr_index");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->d_state[h->state_cur] + first, in, sizeof(fmb_stream_state) * (size_t) count, cudaMemcpyHostToDevice));
+    float *de = (float *) malloc(sizeof(float) * 2 * (size_t) (count ? count : 1));
+    if (!de) return set_err(FMB_ERR_NOMEM, "state");
+    for (int i = 0; i < count; ++i) { de[2 * i] = in[i].deemph_l; de[2 * i + 1] = in[i].deemph_r; }
+    cudaError_t e = cudaMemcpy(h->d_de_state + 2 * first, de, sizeof(float) * 2 * (size_t) count, cudaMemcpyHostToDevice);
+    free(de);
+    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "cudaMemcpy de_state", e);
+    h->phase = prev_lpr_index;
+    h->blocks_done = blocks_done;
+    return FMB_OK;
+}
+
+int fmb_get_tables(const fmb_handle *h, float *fb, float *fm, float *fp, float *fs, float *misc)
+{
+    if (!h || !fb || !fm || !fp || !fs || !misc) return set_err(FMB_ERR_ARG, "NULL argument");
+    const int taps = h->cfg.size >> 1;
+    memcpy(fb, h->tab.chan, sizeof h->tab.chan);
+    memcpy(fm, h->tab.fm, sizeof(float) * taps);
+    memcpy(fp, h->tab.fp, sizeof(float) * taps);
+    memcpy(fs, h->tab.fs, sizeof(float) * taps);
+    misc[0] = h->tab.swf; misc[1] = h->tab.cwf; misc[2] = h->tab.lambda; misc[3] = h->tab.pcm_scale;
+    return FMB_OK;
+}
+
+int fmb_debug_enable(fmb_handle *h, int on)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (on && !h->d_dem) CU(cudaMalloc(&h->d_dem, sizeof(float) * (size_t) h->n_dem * h->cfg.n_streams));
+    h->debug = on ? 1 : 0;
+    return FMB_OK;
+}
+
+int fmb_debug_read(fmb_handle *h, float *dem_host, size_t dem_pitch, float *lr_host, size_t lr_pitch)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    if (!h->debug || !h->d_dem) return set_err(FMB_ERR_STATE, "debug taps not enabled");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (dem_host) {
+        if (dem_pitch < (size_t) h->n_dem) return set_err(FMB_ERR_ARG, "dem_pitch too small");
+        CU(cudaMemcpy2D(dem_host, dem_pitch * 4, h->d_dem, (size_t) h->n_dem * 4, (size_t) h->n_dem * 4,
+                        (size_t) h->cfg.n_streams, cudaMemcpyDeviceToHost));
+    }
+    if (lr_host && h->last_n_out > 0) {
+        if (lr_pitch < (size_t) h->last_n_out) return set_err(FMB_ERR_ARG, "lr_pitch too small");
+        CU(cudaMemcpy2D(lr_host, lr_pitch * 4, h->d_lr[h->last_lr], (size_t) h->lr_pitch * 4, (size_t) h->last_n_out * 4,
+                        (size_t) h->cfg.n_streams, cudaMemcpyDeviceToHost));
+    }
+    return FMB_OK;
+}
+
+int fmb_profile_enable(fmb_handle *h, int on)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (on) { int rc = ensure_profile_events(h); if (rc != FMB_OK) return rc; }
+    h->profile = on ? 1 : 0;
+    return FMB_OK;
+}
+
+int fmb_profile_reset(fmb_handle *h)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; ++k) { h->pcount[k] = 0; h->pms[k] = 0; h->plaunch[k] = 0; }
+    return FMB_OK;
+}
+
+int fmb_profile_read(fmb_handle *h, double ms_total[2], int launches[2])
+{
+    if (!h || !ms_total || !launches) return set_err(FMB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    int rc = fold_profile(h);
+    if (rc != FMB_OK) return rc;
+    for (int k = 0; k < 2; ++k) { ms_total[k] = h->pms[k]; launches[k] = h->plaunch[k]; }
+    return FMB_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,81 @@
+/*
+ * fmb_internal.h -- shared between the host API (fmb_api.cu), the filter design
+ * (fm_design.c) and the kernels (fmb_kernels.cu).  Not installed.
+ */
+#ifndef FMB_INTERNAL_H
+#define FMB_INTERNAL_H
+
+#include "fmb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMB_MAX_TAPS 64 /* size/2 */
+
+/*
+ * Filter tables, passed to the kernels by value (kernel parameter space is a
+ * constant bank, so unrolled loops read taps as immediate constant operands).
+ */
+typedef struct fmb_tables {
+    float chan[16];        /* init_lp_f32 half filter (reference :241-251)                       */
+    float chan_s[16];      /* chan * 2^-7 (exact): applied to (byte - 127.5) instead of /128    */
+    float fm[FMB_MAX_TAPS];/* audio low-pass half       (:444-445)                               */
+    float fp[FMB_MAX_TAPS];/* pilot band-pass half      (:447-448)                               */
+    float fs[FMB_MAX_TAPS];/* L-R band-pass half        (:450-451)                               */
+    float swf, cwf;        /* sin/cos of 2*pi*19000/rate_in (:421-423)                           */
+    float lambda;          /* de-emphasis pole (:1577)                                           */
+    float pcm_scale;       /* volume * 32768 (:717)                                              */
+} fmb_tables;
+
+/* Host-side design with glibc sinf/cosf/exp, the reference's float expressions. */
+int fmb_design_tables(const fmb_config *cfg, fmb_tables *t);
+
+/* Kernel geometry (see DESIGN.md "Kernel 1"). */
+#define FMB_NT 256                 /* threads per CTA                                   */
+#define FMB_RUN 8                  /* consecutive demodulated samples per thread         */
+#define FMB_NSUB (FMB_NT * FMB_RUN)/* demodulated samples per sub-tile (2048)            */
+#define FMB_WARM 256               /* recomputed lead-in of a segment that is not first  */
+
+typedef struct fmb_kparams {
+    const uint8_t *iq;             /* [stream][iq_pitch] bytes, this step's block        */
+    long long iq_pitch;
+    const fmb_stream_state *st_in; /* carried state, read by segment 0                   */
+    fmb_stream_state *st_out;      /* carried state, written by the last segment          */
+    float *lr;                     /* decoder output, f32 [stream][lr_pitch]              */
+    long long lr_pitch;
+    float *dem_dump;               /* optional discriminator tap [stream][dem_pitch]      */
+    long long dem_pitch;
+    int n_streams;
+    int segs;                      /* time segments per stream                            */
+    int seg_len;                   /* demodulated samples per segment                     */
+    int n_dem;                     /* demodulated samples per stream this step            */
+    int slow, fast, phase0;        /* resampler: rate_out2, rate_out, prev_lpr_index      */
+    int dec;                       /* fast/slow when integral, else 0                     */
+    int dec_c0;                    /* tick at relative i  <=>  (i + dec_c0) % dec == dec-1 */
+    int quirk;                     /* patch d[1] with R of the tick at i=0   */
+} fmb_kparams;
+
+typedef struct fmb_dparams {
+    const float *lr;
+    long long lr_pitch;
+    int16_t *pcm;
+    long long pcm_pitch;
+    float *de_state;               /* [stream][2] de-emphasis memories                    */
+    int n_streams;
+    int n_out;                     /* int16 values per stream                             */
+    int pairs;                     /* 1: L,R interleaved (lpr.mode == 2)                  */
+    int do_deemph;
+    float lambda, pcm_scale;
+} fmb_dparams;
+
+/* Launchers (fmb_kernels.cu).  `stream` is a cudaStream_t.  Return cudaError_t as int. */
+int fmb_launch_demod(const fmb_config *cfg, const fmb_kparams *p, const fmb_tables *t, void *stream);
+int fmb_launch_deemph(const fmb_dparams *p, void *stream);
+/* 0 when (mode,size) has a compiled kernel. */
+int fmb_demod_supported(int mode, int size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
