@@ -364,7 +364,7 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     } else {
         h->max_out = h->n_dem;
     }
-    h->lr_pitch = ((long long) h->max_out + 7) & ~7LL;
+    h->lr_pitch = ((long long) h->max_out + 127) & ~127LL; /* whole de-emphasis stages */
 
     const size_t st_bytes = sizeof(fmb_stream_state) * (size_t) cfg->n_streams;
 #define CUH(call)                                                                                   \

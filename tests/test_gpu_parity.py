@@ -1,0 +1,247 @@
+"""Parity of the CUDA path (through the C ABI, libfmb.so) with the CPU oracle and with the PCM
+the reference's own code produced (tests/golden).  Bar: BIT-EXACT int16 PCM and bit-exact float
+stage outputs in FMB_PRECISION_EXACT; +-1 LSB int16 in FMB_PRECISION_FMA (tolerance stated in
+BASELINE.json's north_star for the floating-point stages)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import rtl_fm_player_b200 as R
+from oracle.oracle_py import PortOracle
+from rtl_fm_player_b200 import _lib as L
+from vectors import B, CASES, CONFIGS, LONG_CASES, make_input, sha
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
+META = json.load(open(os.path.join(HERE, "golden", "golden_meta.json")))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def same_floats(a, b):
+    """bit-identical, or identical up to the sign of zero (which no later stage can observe)."""
+    return np.array_equal(bits(a), bits(b)) or np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def cfg_for(name, **kw):
+    c = dict(CONFIGS[name])
+    c.update(kw)
+    return R.DemodConfig(**c)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_cuda_pcm_equals_reference_golden_and_oracle_stages(case):
+    cid, cfg, kind, stream, blocks = case
+    iq = make_input(cfg, kind, stream, blocks)
+    assert sha(iq) == META["cases"][cid]["input_sha256"]
+    port = PortOracle(**CONFIGS[cfg])
+    got = []
+    with R.FmBatch(cfg_for(cfg, n_streams=1)) as fb:
+        fb.debug_enable(True)
+        for b in range(blocks):
+            blk = iq[None, b * B:(b + 1) * B]
+            assert fb.next_out_count() == META["cases"][cid]["counts"][b]
+            pcm = fb.process(blk)
+            dem, lr = fb.debug_read()
+            p_or, st = port.block(blk[0], stages=True)
+            assert same_floats(dem[0], st["dem"]), f"block {b}: discriminator output differs"
+            assert same_floats(lr[0, :len(st["lr"])], st["lr"]), f"block {b}: decoder output differs"
+            assert np.array_equal(pcm[0], p_or), f"block {b}: PCM differs from the oracle"
+            got.append(pcm[0])
+    assert np.array_equal(np.concatenate(got), GOLD[cid]), "PCM differs from the reference's own output"
+
+
+@pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
+def test_configs_0_and_1_ten_second_capture(case):
+    """BASELINE.json configs[0] (mono) and [1] (stereo): 10 s single-channel capture, sha256 of the
+    PCM must equal the reference's."""
+    cid, cfg, kind, stream, blocks = case
+    iq = make_input(cfg, kind, stream, blocks)
+    m = META["long"][cid]
+    with R.FmBatch(cfg_for(cfg, n_streams=1)) as fb:
+        pcm = fb.run(np.concatenate([iq, np.zeros(30720000 - blocks * B, np.uint8)])[None, :])
+    assert pcm.shape[1] == m["n_pcm"] and sha(pcm[0]) == m["pcm_sha256"]
+
+
+def test_config_2_sixty_four_streams_each_vs_its_own_oracle():
+    n, blocks = 64, 3
+    kw = CONFIGS["stereo192"]
+    iq = R.synth.batch("fm_stereo", n, 192000, 0, blocks * B // 2)
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        pcm = fb.run(iq)
+    for s in range(n):
+        assert np.array_equal(pcm[s], PortOracle(**kw).run(iq[s])), f"stream {s}"
+
+
+@pytest.mark.parametrize("segs", [1, 2, 4, 8])
+@pytest.mark.parametrize("cfgname,kind", [("stereo192", "random"), ("mono192", "fm_mono"), ("stereo240", "random")])
+def test_time_segmentation_does_not_change_the_result(cfgname, kind, segs):
+    blocks = 6 if cfgname == "stereo240" else 2
+    iq = np.stack([make_input(cfgname, kind, s, blocks) for s in range(2)])
+    with R.FmBatch(cfg_for(cfgname, n_streams=2, segments=segs)) as fb:
+        pcm = fb.run(iq)
+    for s in range(2):
+        assert np.array_equal(pcm[s], PortOracle(**CONFIGS[cfgname]).run(iq[s]))
+
+
+@pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("stereo192", "random"), ("mono192", "random"),
+                                          ("stereo240", "fm_stereo")])
+def test_fma_precision_within_one_lsb(cfgname, kind):
+    blocks = 6 if cfgname == "stereo240" else 3
+    iq = make_input(cfgname, kind, 3, blocks)[None, :]
+    with R.FmBatch(cfg_for(cfgname, n_streams=1, precision=R.FMB_PRECISION_FMA)) as fb:
+        pcm = fb.run(iq)[0].astype(np.int32)
+    want = PortOracle(**CONFIGS[cfgname]).run(iq[0]).astype(np.int32)
+    assert pcm.shape == want.shape
+    assert np.abs(pcm - want).max() <= 1      # tolerance: +-1 LSB of int16 PCM
+
+
+def test_carried_state_equals_the_oracles_and_resumes_bit_exactly():
+    """fmb_get_state mirrors the state fields of demod_state; a new handle restored from it
+    continues bit-exactly (checkpoint/resume)."""
+    cfgname = "stereo240"
+    iq = np.stack([make_input(cfgname, "random", s, 5) for s in range(3)])
+    orc = [PortOracle(**CONFIGS[cfgname]) for _ in range(3)]
+    with R.FmBatch(cfg_for(cfgname, n_streams=3)) as fb:
+        for b in range(3):
+            fb.process(iq[:, b * B:(b + 1) * B])
+            for s in range(3):
+                orc[s].block(iq[s, b * B:(b + 1) * B])
+        st, phase, blocks_done = fb.get_state()
+        for s in range(3):
+            o, oph, obl = orc[s].state()
+            assert phase == oph and blocks_done == obl == 3
+            for f, n in (("lowpass_tb", 48), ("br", 128), ("bm", 128), ("bs", 128)):
+                of = "tb" if f == "lowpass_tb" else f
+                assert same_floats(np.frombuffer(getattr(st[s], f), np.float32), np.frombuffer(getattr(o, of), np.float32)), (s, f)
+            for f in ("pre_r", "pre_j", "pp", "deemph_l", "deemph_r"):
+                assert np.float32(getattr(st[s], f)) == np.float32(getattr(o, f)), (s, f)
+        rest = [fb.process(iq[:, b * B:(b + 1) * B]) for b in (3, 4)]
+    with R.FmBatch(cfg_for(cfgname, n_streams=3)) as fb2:
+        fb2.set_state(st, phase, blocks_done)
+        rest2 = [fb2.process(iq[:, b * B:(b + 1) * B]) for b in (3, 4)]
+    for a, b_ in zip(rest, rest2):
+        assert np.array_equal(a, b_)
+    for s in range(3):
+        assert np.array_equal(rest[0][s], orc[s].block(iq[s, 3 * B:4 * B]))
+        assert np.array_equal(rest[1][s], orc[s].block(iq[s, 4 * B:5 * B]))
+
+
+def test_reset_restarts_the_stream():
+    iq = make_input("stereo192", "random", 2, 2)[None, :]
+    with R.FmBatch(cfg_for("stereo192", n_streams=1)) as fb:
+        a = fb.run(iq)
+        fb.reset()
+        b = fb.run(iq)
+    assert np.array_equal(a, b)
+
+
+def test_three_host_paths_agree():
+    """fmb_process, fmb_submit/fmb_wait (pipelined) and fmb_process_device give the same PCM."""
+    import torch
+    n, blocks = 5, 4
+    iq = np.stack([make_input("stereo192", "fm_stereo", s, blocks) for s in range(n)])
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        ref = fb.run(iq)
+    # pipelined, pinned
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        hin = [torch.from_numpy(iq[:, b * B:(b + 1) * B].copy()).pin_memory() for b in range(blocks)]
+        hout = [torch.zeros((n, 8192), dtype=torch.int16).pin_memory() for _ in range(blocks)]
+        tickets = []
+        for b in range(blocks):
+            if len(tickets) == L.FMB_PIPE_DEPTH:
+                fb.wait(tickets.pop(0))
+            tickets.append(fb.submit(hin[b].data_ptr(), B, hout[b].data_ptr(), 8192))
+        for t in tickets:
+            fb.wait(t)
+        piped = np.concatenate([h.numpy() for h in hout], axis=1)
+    assert np.array_equal(piped, ref)
+    # device resident
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        d_in = torch.from_numpy(iq).cuda()
+        d_out = torch.zeros((blocks, n, 8192), dtype=torch.int16, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for b in range(blocks):
+            fb.process_device(d_in.data_ptr() + b * B, iq.shape[1], d_out[b].data_ptr(), 8192, st)
+        fb.join(st)
+        torch.cuda.synchronize()
+        dev = np.concatenate([d_out[b].cpu().numpy() for b in range(blocks)], axis=1)
+    assert np.array_equal(dev, ref)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 97])
+def test_ragged_stream_counts(n):
+    iq = np.stack([make_input("stereo192", "random", s % 4, 1) for s in range(n)])
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        pcm = fb.run(iq)
+    want = [PortOracle(**CONFIGS["stereo192"]).run(iq[s]) for s in range(4)]
+    for s in range(n):
+        assert np.array_equal(pcm[s], want[s % 4])
+
+
+def test_small_blocks_equal_one_reference_block():
+    """block_bytes is any multiple of 32768; at 192 kHz (no in-place quirk) the split is invisible."""
+    iq = make_input("stereo192", "random", 12, 2)[None, :]
+    with R.FmBatch(cfg_for("stereo192", n_streams=1, block_bytes=32768)) as fb:
+        small = fb.run(iq)
+    assert np.array_equal(small[0], PortOracle(**CONFIGS["stereo192"]).run(iq[0]))
+
+
+@pytest.mark.parametrize("offset", [0, 1])
+def test_config_3_full_size_1024_streams(offset):
+    """BASELINE.json configs[3]: 1024 streams, rotate and offset paths.  16 distinct channels are
+    each checked against the oracle; the replicas must be identical to their originals."""
+    n, uniq, blocks = 1024, 16, 2
+    name = "stereo192_off" if offset else "stereo192"
+    iq = R.synth.batch("fm_stereo", n, 192000, offset, blocks * B // 2, unique=uniq)
+    with R.FmBatch(cfg_for(name, n_streams=n)) as fb:
+        pcm = fb.run(iq)
+    for s in range(uniq):
+        assert np.array_equal(pcm[s], PortOracle(**CONFIGS[name]).run(iq[s])), s
+    assert np.array_equal(pcm.reshape(n // uniq, uniq, -1), np.broadcast_to(pcm[:uniq], (n // uniq, uniq, pcm.shape[1])))
+
+
+def test_config_4_maximum_size_8192_streams_on_one_gpu():
+    """8192 streams (the whole configs[4] batch on ONE device, 2 GiB of IQ per step)."""
+    n, uniq = 8192, 8
+    iq = R.synth.batch("fm_stereo", n, 192000, 0, B // 2, unique=uniq)
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        pcm = fb.process(iq)
+    for s in range(uniq):
+        assert np.array_equal(pcm[s], PortOracle(**CONFIGS["stereo192"]).run(iq[s])), s
+    sums = pcm.astype(np.int64).sum(axis=1).reshape(n // uniq, uniq)     # checksum of checksums
+    assert (sums == sums[0]).all()
+
+
+def test_kernels_really_launch_and_errors_are_loud():
+    iq = make_input("stereo192", "fm_stereo", 0, 1)[None, :]
+    before = R.launch_count()
+    with R.FmBatch(cfg_for("stereo192", n_streams=1)) as fb:
+        fb.process(iq)
+        assert R.launch_count() - before == 2           # demod + de-emphasis kernels
+        pcm = np.zeros((1, 16), np.int16)
+        rc = fb._lib.fmb_process(fb._h, iq.ctypes.data, B, pcm.ctypes.data, 16, None)
+        assert rc == L.FMB_ERR_ARG                       # pcm_pitch < out count
+        assert fb._lib.fmb_wait(fb._h, 12345, None) == L.FMB_ERR_STATE
+    # rate ratio < 3 with a resampler phase where the reference's in-place stereo output would
+    # overwrite unread input beyond the emulated first-sample case: refused, never silently wrong
+    with R.FmBatch(cfg_for("stereo192", n_streams=1, rate_in=100000)) as fb:
+        st, _, _ = fb.get_state()
+        fb.set_state(st, 60000, 0)
+        with pytest.raises(R.FmbError) as e:
+            fb.process(iq)
+        assert e.value.code == L.FMB_ERR_UNSUPPORTED
+
+
+def test_low_rate_ratio_supported_where_hazard_free():
+    iq = make_input("stereo192", "random", 1, 1)[None, :]
+    kw = dict(CONFIGS["stereo192"], rate_in=100000)
+    with R.FmBatch(R.DemodConfig(n_streams=1, **kw)) as fb:
+        pcm = fb.process(iq)
+    assert np.array_equal(pcm[0], PortOracle(**kw).run(iq[0]))
