@@ -144,7 +144,13 @@ typedef struct fmb_stream_state {
     float bs[FMB_HIST];      /* last FMB_HIST demodulated L-R samples             (lpr.bs ring)     */
     float pp;                /* previous pilot band-pass output              (lpr.pp)              */
     float deemph_l, deemph_r;/* de-emphasis memories                         (deemph_l/r_f32)      */
-    float reserved[3];
+    /* Not in the reference: the last 32 raw IQ samples of the previous block.  When raw_valid != 0
+     * the kernels rebuild lowpass_tb / pre_r / pre_j from these bytes on their normal fast path;
+     * when 0 (stream start, or a state filled in from a reference demod_state, which only has the
+     * floats) the float fields above are used instead.  fmb_get_state always returns both. */
+    int raw_valid;
+    float reserved[2];
+    unsigned char raw_tail[64]; /* at a 16-byte aligned offset (1760) */
 } fmb_stream_state;
 
 /* Copies out/in the state of streams [first, first+count).  prev_lpr_index (the

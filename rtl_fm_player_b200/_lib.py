@@ -42,7 +42,8 @@ class FmbStreamState(C.Structure):
     _fields_ = [
         ("lowpass_tb", C.c_float * 48), ("pre_r", C.c_float), ("pre_j", C.c_float),
         ("br", C.c_float * FMB_HIST), ("bm", C.c_float * FMB_HIST), ("bs", C.c_float * FMB_HIST),
-        ("pp", C.c_float), ("deemph_l", C.c_float), ("deemph_r", C.c_float), ("reserved", C.c_float * 3),
+        ("pp", C.c_float), ("deemph_l", C.c_float), ("deemph_r", C.c_float), ("raw_valid", C.c_int),
+        ("reserved", C.c_float * 2), ("raw_tail", C.c_ubyte * 64),
     ]
 
 

@@ -111,7 +111,8 @@ class FmBatch:
         n = self.next_out_count()
         pitch = max(8, (n + 7) & ~7)
         pcm = np.empty((self.cfg.n_streams, pitch), dtype=np.int16)
-        L.check(self._lib.fmb_process(self._h, iq.ctypes.data, iq.strides[0], pcm.ctypes.data, pitch, None),
+        iq_pitch = iq.strides[0] if iq.shape[0] > 1 else self.cfg.block_bytes   # a 1-row view may carry stride 0
+        L.check(self._lib.fmb_process(self._h, iq.ctypes.data, iq_pitch, pcm.ctypes.data, pitch, None),
                 "fmb_process")
         return pcm[:, :n]
 
@@ -178,8 +179,14 @@ class FmBatch:
     def _check_iq(self, iq: np.ndarray) -> np.ndarray:
         if iq.dtype != np.uint8 or iq.ndim != 2 or iq.shape != (self.cfg.n_streams, self.cfg.block_bytes):
             raise ValueError(f"iq must be uint8 [{self.cfg.n_streams}, {self.cfg.block_bytes}], got {iq.dtype} {iq.shape}")
-        if iq.strides[1] != 1:
-            iq = np.ascontiguousarray(iq)
+        if iq.strides[1] != 1 or (iq.shape[0] > 1 and (iq.strides[0] < self.cfg.block_bytes or iq.strides[0] % 16)) or iq.ctypes.data % 16:
+            iq = np.ascontiguousarray(iq)       # (also a 1-stream view made with iq[None, ...] has stride 0)
+            if iq.ctypes.data % 16:
+                buf = np.empty(iq.size + 16, dtype=np.uint8)
+                off = (-buf.ctypes.data) % 16
+                aligned = buf[off:off + iq.size].reshape(iq.shape)
+                aligned[...] = iq
+                iq = aligned
         return iq
 
 

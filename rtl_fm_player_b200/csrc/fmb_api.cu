@@ -9,12 +9,16 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "fmb_internal.h"
+
+static_assert(offsetof(fmb_stream_state, raw_tail) % 16 == 0 && sizeof(fmb_stream_state) % 16 == 0,
+              "raw_tail is the source/destination of 16-byte copies");
 
 namespace {
 
@@ -52,7 +56,7 @@ struct fmb_handle {
     fmb_config cfg;
     fmb_tables tab;
     int n_dem;                 /* demodulated samples per stream per step */
-    int segs, seg_len;
+    int grid;                  /* CTAs of the demod kernel */
     int max_out;
     /* resampler bookkeeping (common to all streams) */
     int phase;                 /* prev_lpr_index */
@@ -129,27 +133,6 @@ bool tick_on_first_sample(const fmb_handle *h, int phase)
     return c.mode == 2 && c.rate_out2 > 0 && (long long) phase + c.rate_out2 >= c.rate_in;
 }
 
-int pick_segments(int n_streams, int n_dem)
-{
-    /* Fill 148 SMs x 2 resident CTAs; each extra segment costs FMB_WARM recomputed samples. */
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = 2 * sms;
-    const int max_segs = n_dem / FMB_NSUB;
-    int best = 1;
-    double best_cost = 1e30;
-    for (int s = 1; s <= max_segs && s <= 8; s *= 2) {
-        if ((n_dem / FMB_NSUB) % s) continue;
-        const double ctas = (double) n_streams * s;
-        const double waves = (double) ((long long) ((ctas + slots - 1) / slots));
-        const double per_cta = (double) n_dem / s + (s > 1 ? FMB_WARM * 2.0 : 0.0);
-        const double cost = waves * per_cta;
-        if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
-    }
-    return best;
-}
-
 void destroy_events(cudaEvent_t *ev, int n)
 {
     if (!ev) return;
@@ -216,8 +199,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     kp.dem_dump = h->debug ? h->d_dem : nullptr;
     kp.dem_pitch = h->n_dem;
     kp.n_streams = c.n_streams;
-    kp.segs = h->segs;
-    kp.seg_len = h->seg_len;
+    kp.grid = h->grid;
     kp.n_dem = h->n_dem;
     if (c.rate_out2 > 0) {
         kp.slow = c.rate_out2; kp.fast = c.rate_in; kp.phase0 = h->phase;
@@ -348,13 +330,30 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     int rc = fmb_design_tables(cfg, &h->tab);
     if (rc != FMB_OK) { delete h; return set_err(rc, "filter design rejected the configuration"); }
     h->n_dem = cfg->block_bytes / 16;
-    h->segs = cfg->segments > 0 ? cfg->segments : pick_segments(cfg->n_streams, h->n_dem);
-    if (h->segs < 1 || (h->n_dem / FMB_NSUB) % h->segs || h->segs > h->n_dem / FMB_NSUB) {
-        delete h;
-        return set_err(FMB_ERR_ARG, "segments must divide block_bytes/32768");
+    {
+        /* CTAs: the n_streams x (block/2048 samples) work units are dealt out evenly ("stream-K").
+         * Default: one CTA per resident slot (SMs x occupancy); cfg.segments > 0 forces n_streams x segments. */
+        const long long units = (long long) cfg->n_streams * (h->n_dem / FMB_NSUB);
+        if (cfg->segments > 0) {
+            if ((h->n_dem / FMB_NSUB) % cfg->segments) {
+                delete h;
+                return set_err(FMB_ERR_ARG, "segments must divide block_bytes/32768");
+            }
+            h->grid = cfg->n_streams * cfg->segments;
+        } else {
+            fmb_config kc = *cfg;
+            if (cfg->rate_out2 <= 0) kc.mode = 0;
+            int occ = 0, sms = 0;
+            cudaError_t e1 = (cudaError_t) fmb_demod_occupancy(&kc, &occ);
+            cudaError_t e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+            if (e1 != cudaSuccess || e2 != cudaSuccess || occ < 1 || sms < 1) {
+                delete h;
+                return set_err(FMB_ERR_CUDA, "occupancy query for the demod kernel", e1 != cudaSuccess ? e1 : e2);
+            }
+            const long long slots = (long long) occ * sms;
+            h->grid = (int) (units < slots ? units : slots);
+        }
     }
-    h->seg_len = h->n_dem / h->segs;
-    h->cfg.segments = h->segs;
     h->phase = 0;
     h->blocks_done = 0;
     /* upper bound of outputs per step */
@@ -382,7 +381,13 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     }
     CUH(cudaMalloc(&h->d_de_state, sizeof(float) * 2 * (size_t) cfg->n_streams));
     CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
-    CUH(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+    {
+        /* the de-emphasis pass runs beside the NEXT step's demod kernel: give it the highest priority
+         * so its few CTAs take the first SM slots that free up instead of queueing behind that grid */
+        int prio_lo = 0, prio_hi = 0;
+        CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUH(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, prio_hi));
+    }
     CUH(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
     CUH(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CUH(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));

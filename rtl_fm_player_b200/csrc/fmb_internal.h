@@ -47,8 +47,7 @@ typedef struct fmb_kparams {
     float *dem_dump;               /* optional discriminator tap [stream][dem_pitch]      */
     long long dem_pitch;
     int n_streams;
-    int segs;                      /* time segments per stream                            */
-    int seg_len;                   /* demodulated samples per segment                     */
+    int grid;                      /* CTAs: the (stream, sub-tile) units are dealt out evenly */
     int n_dem;                     /* demodulated samples per stream this step            */
     int slow, fast, phase0;        /* resampler: rate_out2, rate_out, prev_lpr_index      */
     int dec;                       /* fast/slow when integral, else 0                     */
@@ -72,6 +71,8 @@ typedef struct fmb_dparams {
 /* Launchers (fmb_kernels.cu).  `stream` is a cudaStream_t.  Return cudaError_t as int. */
 int fmb_launch_demod(const fmb_config *cfg, const fmb_kparams *p, const fmb_tables *t, void *stream);
 int fmb_launch_deemph(const fmb_dparams *p, void *stream);
+/* resident CTAs per SM of the kernel this configuration selects */
+int fmb_demod_occupancy(const fmb_config *cfg, int *ctas_per_sm);
 /* 0 when (mode,size) has a compiled kernel. */
 int fmb_demod_supported(int mode, int size);
 
