@@ -177,6 +177,11 @@ int fmb_profile_enable(fmb_handle *h, int on);
 int fmb_profile_reset(fmb_handle *h);
 int fmb_profile_read(fmb_handle *h, double ms_total[2], int launches[2]);
 
+/* Diagnostic: the de-emphasis kernel runs its recurrence speculatively in time and verifies it
+ * (DESIGN.md "Kernel 2"); this is the number of 1024-value chunks, since fmb_create, whose
+ * verification failed and which were therefore redone sequentially.  Results are exact either way. */
+int fmb_deemph_fallbacks(fmb_handle *h, unsigned long long *count);
+
 const char *fmb_last_error(void);
 /* Number of CUDA kernels this library has launched in this process. */
 long fmb_launch_count(void);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "fmb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fmb_profile_reset": (C.c_int, [C.c_void_p]),
     "fmb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fmb_deemph_fallbacks": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "fmb_last_error": (C.c_char_p, []),
     "fmb_launch_count": (C.c_long, []),
     "fmb_version": (C.c_char_p, []),

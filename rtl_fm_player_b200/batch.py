@@ -163,6 +163,12 @@ class FmBatch:
         L.check(self._lib.fmb_debug_read(self._h, dem.ctypes.data, n_dem, lr.ctypes.data, lr.shape[1]), "fmb_debug_read")
         return dem, lr
 
+    def deemph_fallbacks(self) -> int:
+        """De-emphasis chunks whose time-speculation failed verification and were redone in order."""
+        n = C.c_ulonglong(0)
+        L.check(self._lib.fmb_deemph_fallbacks(self._h, C.byref(n)), "fmb_deemph_fallbacks")
+        return int(n.value)
+
     def profile_enable(self, on: bool = True) -> None:
         L.check(self._lib.fmb_profile_enable(self._h, int(on)), "fmb_profile_enable")
 

@@ -65,6 +65,7 @@ struct fmb_handle {
     fmb_stream_state *d_state[2] = {nullptr, nullptr};
     int state_cur = 0;
     float *d_de_state = nullptr;     /* [n_streams][2] */
+    unsigned int *d_fallbacks = nullptr; /* de-emphasis chunks redone sequentially (diagnostic) */
     float *d_lr[2] = {nullptr, nullptr};
     long long lr_pitch = 0;
     int lr_cur = 0;
@@ -238,6 +239,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     dp.do_deemph = c.deemph != 0.0;
     dp.lambda = h->tab.lambda;
     dp.pcm_scale = h->tab.pcm_scale;
+    dp.fallbacks = h->d_fallbacks;
     if (prof) CU(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
     e = (cudaError_t) fmb_launch_deemph(&dp, h->s_aux);
     if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_deemph_kernel launch", e);
@@ -381,6 +383,8 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     }
     CUH(cudaMalloc(&h->d_de_state, sizeof(float) * 2 * (size_t) cfg->n_streams));
     CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
+    CUH(cudaMalloc(&h->d_fallbacks, sizeof(unsigned int)));
+    CUH(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned int)));
     {
         /* the de-emphasis pass runs beside the NEXT step's demod kernel: give it the highest priority
          * so its few CTAs take the first SM slots that free up instead of queueing behind that grid */
@@ -410,6 +414,7 @@ int fmb_destroy(fmb_handle *h)
         if (h->ev_deemph[i]) cudaEventDestroy(h->ev_deemph[i]);
     }
     if (h->d_de_state) cudaFree(h->d_de_state);
+    if (h->d_fallbacks) cudaFree(h->d_fallbacks);
     if (h->d_dem) cudaFree(h->d_dem);
     for (auto &s : h->slot) {
         if (s.d_iq) cudaFree(s.d_iq);
@@ -594,6 +599,17 @@ int fmb_get_tables(const fmb_handle *h, float *fb, float *fm, float *fp, float *
     memcpy(fp, h->tab.fp, sizeof(float) * taps);
     memcpy(fs, h->tab.fs, sizeof(float) * taps);
     misc[0] = h->tab.swf; misc[1] = h->tab.cwf; misc[2] = h->tab.lambda; misc[3] = h->tab.pcm_scale;
+    return FMB_OK;
+}
+
+int fmb_deemph_fallbacks(fmb_handle *h, unsigned long long *count)
+{
+    if (!h || !count) return set_err(FMB_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    unsigned int v = 0;
+    CU(cudaMemcpy(&v, h->d_fallbacks, sizeof v, cudaMemcpyDeviceToHost));
+    *count = v;
     return FMB_OK;
 }
 

@@ -66,6 +66,8 @@ typedef struct fmb_dparams {
     int pairs;                     /* 1: L,R interleaved (lpr.mode == 2)                  */
     int do_deemph;
     float lambda, pcm_scale;
+    unsigned int *fallbacks;       /* device counter: chunks whose time-speculation failed and
+                                      were redone sequentially (diagnostic; may be NULL)   */
 } fmb_dparams;
 
 /* Launchers (fmb_kernels.cu).  `stream` is a cudaStream_t.  Return cudaError_t as int. */

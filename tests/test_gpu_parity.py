@@ -245,3 +245,44 @@ def test_low_rate_ratio_supported_where_hazard_free():
     with R.FmBatch(R.DemodConfig(n_streams=1, **kw)) as fb:
         pcm = fb.process(iq)
     assert np.array_equal(pcm[0], PortOracle(**kw).run(iq[0]))
+
+
+def test_deemphasis_speculation_is_verified_and_falls_back_on_digital_silence():
+    """Kernel 2 runs the IIR speculatively in time and verifies every junction.  On a real FM
+    signal in steady state the verification passes (no sequential redo); on constant bytes the
+    true state sticks at a denormal, the speculation fails, every chunk is redone in order --
+    and the PCM is the oracle's in both cases."""
+    blocks = 4
+    for kind in ("fm_stereo", "const127"):
+        iq = make_input("stereo192", kind, 0, blocks)[None, :]
+        orc = PortOracle(**CONFIGS["stereo192"])
+        with R.FmBatch(cfg_for("stereo192", n_streams=1)) as fb:
+            counts = []
+            for b in range(blocks):
+                pcm = fb.process(iq[:, b * B:(b + 1) * B])
+                assert np.array_equal(pcm[0], orc.block(iq[0, b * B:(b + 1) * B]))
+                counts.append(fb.deemph_fallbacks())
+        if kind == "fm_stereo":
+            assert counts[-1] == counts[0] <= 2, counts      # at most the start-up transient
+        else:
+            assert counts[-1] >= 8 * (blocks - 1), counts    # 8 chunks of 1024 values per block
+
+
+@pytest.mark.parametrize("pitch_extra", [0, 1, 3, 8])
+def test_unaligned_pcm_pitch(pitch_extra):
+    """PCM rows that are not 16-byte aligned take the scalar store path."""
+    n = 3
+    iq = np.stack([make_input("stereo240", "random", s, 2) for s in range(n)])
+    want = [PortOracle(**CONFIGS["stereo240"]).run(iq[s]) for s in range(n)]
+    with R.FmBatch(cfg_for("stereo240", n_streams=n)) as fb:
+        got = []
+        for b in range(2):
+            cnt = fb.next_out_count()
+            pitch = cnt + pitch_extra
+            pcm = np.zeros((n, pitch), np.int16)
+            blk = np.ascontiguousarray(iq[:, b * B:(b + 1) * B])
+            L.check(fb._lib.fmb_process(fb._h, blk.ctypes.data, B, pcm.ctypes.data, pitch, None), "fmb_process")
+            got.append(pcm[:, :cnt])
+    got = np.concatenate(got, axis=1)
+    for s in range(n):
+        assert np.array_equal(got[s], want[s])

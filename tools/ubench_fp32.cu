@@ -49,6 +49,39 @@ __global__ void __launch_bounds__(256) k(float *out, int iters, float a, float b
                 x[i] = __fadd_rn(v.x, b); x[i + 1] = __fadd_rn(v.y, b);
             }
         }
+        else if (MODE == 6) { // FADD reg,reg (both operands registers, operands rotate)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = __fadd_rn(x[i], x[(i + 5) & 15]);
+        } else if (MODE == 7) { // FMUL reg,reg
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = __fmul_rn(x[i], x[(i + 5) & 15]);
+        } else if (MODE == 8) { // FFMA reg,reg,reg
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = __fmaf_rn(x[i], x[(i + 5) & 15], x[(i + 11) & 15]);
+        } else if (MODE == 9) { // the bit-exact FIR tap: v = a+b (reg,reg); acc_j += v*c_j (3 filters, coef constant)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = __fadd_rn(x[i], x[12 + ((i + 1) & 3)]);
+                x[8 + i] = __fadd_rn(x[8 + i], __fmul_rn(v, a));
+                x[12 + i] = __fadd_rn(x[12 + i], __fmul_rn(v, b));
+            }
+        } else if (MODE == 10) { // MODE 9 + one PRMT (alu pipe) per 5 FP ops
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = __fadd_rn(x[i], x[12 + ((i + 1) & 3)]);
+                x[8 + i] = __fadd_rn(x[8 + i], __fmul_rn(v, a));
+                x[12 + i] = __fadd_rn(x[12 + i], __fmul_rn(v, b));
+                x[i] = __uint_as_float(__byte_perm(__float_as_uint(x[i]), 0x3f800000u, 0x7610 + it));
+            }
+        } else if (MODE == 11) { // packed tap: v2 = add2; p2 = mul2(v2, c2); scalar adds (no FFMA2 contraction possible)
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+                const float2 v = __fadd2_rn(make_float2(x[i], x[i + 1]), make_float2(x[12 + ((i + 2) & 3)], x[13 + ((i + 2) & 3)]));
+                const float2 pa = __fmul2_rn(v, a2), pb = __fmul2_rn(v, b2);
+                x[8 + i] = __fadd_rn(x[8 + i], pa.x); x[9 + i] = __fadd_rn(x[9 + i], pa.y);
+                x[12 + i] = __fadd_rn(x[12 + i], pb.x); x[13 + i] = __fadd_rn(x[13 + i], pb.y);
+            }
+        }
     }
     float s = 0;
 #pragma unroll
@@ -99,6 +132,12 @@ int main()
     run<2>("packed FFMA2 (1 op/value)", 16);
     run<3>("packed FMUL2, FADD2 independent", 16);
     run<5>("packed FMUL2 -> 2x scalar FADD", 32);
+    run<6>("scalar FADD reg,reg", 16);
+    run<7>("scalar FMUL reg,reg", 16);
+    run<8>("scalar FFMA reg,reg,reg", 16);
+    run<9>("FIR tap scalar: 4x(FADD + 2 FMUL + 2 FADD)", 20);
+    run<10>("FIR tap scalar + 4 PRMT (PRMT not counted)", 20);
+    run<11>("FIR tap packed: FADD2 + 2 FMUL2 + 4 FADD (x2)", 20);
     const int n = 1 << 20;
     float *h = (float *) malloc(3 * n * 4);
     srand(1);
