@@ -69,6 +69,8 @@ typedef struct fmb_config {
     int emulate_inplace_quirk; /* 1 (default): reproduce the reference's in-place overwrite when a
                                   stereo tick falls on the first sample of a block (:593-597;
                                   SURVEY.md A.7).  0: ideal decoder                                 */
+    float deemph_lambda;/* 0 (default): pole = (float)exp(-1/(rate_out2*deemph)) as main() computes it
+                           (:1577).  > 0: use this value (the drop-in passes demod_state.deemph_lambda) */
 } fmb_config;
 
 typedef struct fmb_handle fmb_handle;
@@ -82,6 +84,9 @@ int fmb_preset_mono_192k(fmb_config *cfg);
 
 int fmb_create(const fmb_config *cfg, fmb_handle **out);
 int fmb_destroy(fmb_handle *h);
+
+/* demod_state.volume may change while the player runs; takes effect from the next process call. */
+int fmb_set_volume(fmb_handle *h, float volume);
 
 /* Back to stream start: every stage's history zero in its own float domain,
  * as after demod_init + init_lp_real_f32 (:1156, :413). */

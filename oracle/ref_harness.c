@@ -169,6 +169,29 @@ long ref_run(void *h, const uint8_t *iq, size_t n_bytes, int16_t *pcm, size_t pc
     return n;
 }
 
+/* The reference's own struct inside an instance: what the drop-in shim (include/fm_dropin.h) is handed. */
+void *ref_demod_state(void *h) { return &((struct ref_inst *) h)->d; }
+
+/* The reference's WAV output: InitWaveOut (:1280-1328) writes the fixed header, the output thread writes
+ * whole CIRCBUFFCLUSTER clusters (:955-1005), CloseWaveOut (:1259-1278) patches the sizes. */
+int ref_wav_header(int mode, unsigned char *out260)
+{
+    if (mode == 2) memcpy(out260, _WAVHeaderStereo, sizeof(_WAVHeaderStereo));
+    else memcpy(out260, _WAVHeaderMono, sizeof(_WAVHeaderMono));
+    return (int) (mode == 2 ? sizeof(_WAVHeaderStereo) : sizeof(_WAVHeaderMono));
+}
+
+int ref_wav_write(const char *path, int mode, const unsigned char *pcm, size_t n_bytes)
+{
+    FILE *f = InitWaveOut((char *) path, mode);
+    size_t off;
+    if (!f) return -1;
+    for (off = 0; off + CIRCBUFFCLUSTER <= n_bytes; off += CIRCBUFFCLUSTER)
+        fwrite(pcm + off, sizeof(char), CIRCBUFFCLUSTER, f);
+    CloseWaveOut(f);
+    return 0;
+}
+
 /* sizeof/offsetof of the reference struct, for pinning include/fm_dropin.h. */
 long ref_layout(int what)
 {

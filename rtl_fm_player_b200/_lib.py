@@ -34,6 +34,7 @@ class FmbConfig(C.Structure):
         ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float),
         ("n_streams", C.c_int), ("block_bytes", C.c_int), ("device", C.c_int),
         ("precision", C.c_int), ("segments", C.c_int), ("emulate_inplace_quirk", C.c_int),
+        ("deemph_lambda", C.c_float),
     ]
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "fmb_create": (C.c_int, [C.POINTER(FmbConfig), C.POINTER(C.c_void_p)]),
     "fmb_destroy": (C.c_int, [C.c_void_p]),
     "fmb_reset": (C.c_int, [C.c_void_p]),
+    "fmb_set_volume": (C.c_int, [C.c_void_p, C.c_float]),
     "fmb_next_out_count": (C.c_int, [C.c_void_p]),
     "fmb_max_out_count": (C.c_int, [C.c_void_p]),
     "fmb_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),

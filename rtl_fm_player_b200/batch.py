@@ -33,6 +33,7 @@ class DemodConfig:
     precision: int = L.FMB_PRECISION_EXACT
     segments: int = 0
     emulate_inplace_quirk: int = 1
+    deemph_lambda: float = 0.0
 
     @classmethod
     def stereo_192k(cls, **kw) -> "DemodConfig":
@@ -91,6 +92,9 @@ class FmBatch:
     # -- queries ----------------------------------------------------------------------------
     def next_out_count(self) -> int:
         return L.check(self._lib.fmb_next_out_count(self._h), "fmb_next_out_count")
+
+    def set_volume(self, volume: float) -> None:
+        L.check(self._lib.fmb_set_volume(self._h, volume), "fmb_set_volume")
 
     def reset(self) -> None:
         L.check(self._lib.fmb_reset(self._h), "fmb_reset")

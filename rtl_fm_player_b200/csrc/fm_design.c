@@ -72,6 +72,7 @@ int fmb_design_tables(const fmb_config *cfg, fmb_tables *t)
     {
         const int out_rate = cfg->rate_out2 > 0 ? cfg->rate_out2 : cfg->rate_in;
         t->lambda = cfg->deemph != 0.0 ? (float) exp(-1.0 / ((double) out_rate * cfg->deemph)) : 0.0f;
+        if (cfg->deemph != 0.0 && cfg->deemph_lambda > 0.0f) t->lambda = cfg->deemph_lambda;
     }
     t->pcm_scale = cfg->volume * 32768.0f; /* :717 */
     return FMB_OK;

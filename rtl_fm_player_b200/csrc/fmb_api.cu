@@ -283,6 +283,7 @@ int fmb_default_config(fmb_config *cfg)
     cfg->precision = FMB_PRECISION_EXACT;
     cfg->segments = 0;
     cfg->emulate_inplace_quirk = 1;
+    cfg->deemph_lambda = 0.0f;
     return FMB_OK;
 }
 
@@ -431,6 +432,14 @@ int fmb_destroy(fmb_handle *h)
     for (int k = 0; k < 2; ++k)
         for (int e = 0; e < 2; ++e) destroy_events(h->pev[k][e], kProfMax);
     delete h;
+    return FMB_OK;
+}
+
+int fmb_set_volume(fmb_handle *h, float volume)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    h->cfg.volume = volume;
+    h->tab.pcm_scale = volume * 32768.0f; /* :717, in float like the reference */
     return FMB_OK;
 }
 

@@ -27,7 +27,7 @@ def declared_symbols():
         src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src):
             n = m.group(1)
-            if n.startswith(("fmb_", "fmsrc_", "fmwav_", "fmdrop_")) or n in DROPIN:
+            if n.startswith(("fmb_", "filesrc_", "fm_wav_", "fm_dropin_")) or n in DROPIN:
                 names.add(n)
     return sorted(names)
 
@@ -39,7 +39,7 @@ DROPIN = {"init_u8_f32_table", "init_lp_f32", "init_lp_real_f32", "deinit_lp_rea
 def test_library_loads_and_exports_every_declared_symbol():
     lib = C.CDLL(R.LIB_PATH)
     syms = declared_symbols()
-    assert len(syms) >= 25
+    assert len(syms) >= 50 and DROPIN <= set(syms)
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, f"declared in include/*.h but not exported: {missing}"
 
