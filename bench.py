@@ -42,6 +42,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(streams, mode, precision):
+    """DRAM bytes per launch of the demod kernel from the committed ncu capture (profiles/demod_traffic.json);
+    only valid for the workload it was captured on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "demod_traffic.json")) as f:
+            t = json.load(f)
+        if streams == 1024 and mode == "stereo" and precision == "exact":
+            return t["traffic"], t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -305,6 +318,7 @@ def run_ours(args):
     deemph_ms = prof["deemph_ms"] / max(prof["deemph_launches"], 1)
     alg = ALG_BYTES[args.mode] * S * SAMPLES_PER_BLOCK           # algorithmic bytes per launch (one rank)
     achieved = alg / (demod_ms * 1e-3) * 1e-9
+    traffic, traffic_src = ncu_traffic(S, args.mode, args.precision)
     clocks = clk.summary()
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * sm_mhz * 1e6                         # FP32 lane-instructions/s at the clock seen under load
@@ -320,7 +334,8 @@ def run_ours(args):
                 "api": "fmb_submit/fmb_wait, pinned host buffers, 2 steps in flight", "pcm_checksum": checksum},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "fmb_demod_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "alg_bytes_per_launch": alg, "peak_source": peak_src,
                      "alg_bytes_per_iq_sample": ALG_BYTES[args.mode], "kernel_ms": demod_ms,
                      "deemph_kernel_ms": deemph_ms,
                      "fp32_pipe": {"ops_per_iq_sample": FP32_OPS_PER_SAMPLE[args.mode], "achieved_Tops": fp32_ach * 1e-12,
