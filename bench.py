@@ -56,16 +56,44 @@ def ncu_traffic(streams, mode, precision):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region, sampled through NVML every ~2 ms
+    (nvidia-smi, one process per sample, is too slow for a region of a few milliseconds; it is the
+    fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.bits = [(pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                         0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        except Exception:
+            self.nvml = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for b in self.bits])
+                    self._stop.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
@@ -86,13 +114,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
