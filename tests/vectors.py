@@ -22,6 +22,12 @@ CONFIGS = {
     "nolpr192": dict(rate_in=192000, rate_out2=0, mode=2, size=90, offset_tuning=0),           # rate_out2 == 0
     "nodeemph192": dict(rate_in=192000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.0),
     "loud192": dict(rate_in=192000, rate_out2=48000, mode=2, size=90, offset_tuning=0, volume=1.5),
+    # general -s / -r values: non-integer resampling ratios, other de-emphasis constants
+    "stereo170_44": dict(rate_in=170000, rate_out2=44100, mode=2, size=90, offset_tuning=0),
+    "stereo256_48": dict(rate_in=256000, rate_out2=48000, mode=2, size=90, offset_tuning=1),
+    "mono240_32": dict(rate_in=240000, rate_out2=32000, mode=1, size=128, offset_tuning=0),
+    "stereo192_us": dict(rate_in=192000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.000075),
+    "stereo100_48": dict(rate_in=100000, rate_out2=48000, mode=2, size=90, offset_tuning=0),  # ratio 2.08
 }
 
 # (case id, config, synth kind, stream id, blocks)
@@ -49,6 +55,12 @@ CASES = [
     ("nolpr192_random", "nolpr192", "random", 2, 2),
     ("nodeemph192_random", "nodeemph192", "random", 8, 3),
     ("loud192_random", "loud192", "random", 9, 3),
+    ("stereo170_44_fm", "stereo170_44", "fm_stereo", 4, 5),
+    ("stereo170_44_random", "stereo170_44", "random", 10, 5),
+    ("stereo256_48_random", "stereo256_48", "random", 11, 5),
+    ("mono240_32_fm", "mono240_32", "fm_mono", 2, 4),
+    ("stereo192_us_fm", "stereo192_us", "fm_stereo", 5, 3),
+    ("stereo100_48_random", "stereo100_48", "random", 12, 2),
 ]
 CASE_BY_ID = {c[0]: c for c in CASES}
 
