@@ -237,6 +237,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = R.lib().fmb_bind_thread_to_device_node(local)   # pinned buffers below become node-local
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -358,7 +359,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * BLOCK * world,
                 "d2h_bytes_per_step": S * n_out * 2 * world, "ms_per_step": e2e_s / K * 1e3,
-                "api": "fmb_submit/fmb_wait, pinned host buffers, 2 steps in flight", "pcm_checksum": checksum},
+                "api": "fmb_submit/fmb_wait, pinned host buffers, 2 steps in flight", "pcm_checksum": checksum,
+                "host_numa_node": numa_node},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "fmb_demod_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

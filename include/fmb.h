@@ -130,6 +130,12 @@ int fmb_submit(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t *
                int *ticket);
 int fmb_wait(fmb_handle *h, int ticket, int *n_out);
 
+/* Host plumbing for the end-to-end path: pin the CALLING thread to the CPUs of the NUMA node the
+ * CUDA device hangs off (sysfs numa_node of its PCI function), so that pinned buffers allocated and
+ * filled by this thread are node-local and H2D/D2H copies do not cross the socket interconnect.
+ * Returns the node (>= 0), or a negative code when the topology is not exposed (nothing changed). */
+int fmb_bind_thread_to_device_node(int device);
+
 /* Pinned host memory without CUDA headers. */
 int fmb_host_alloc(void **ptr, size_t bytes);
 int fmb_host_free(void *ptr);

@@ -142,6 +142,7 @@ int main(int argc, char **argv)
     pthread_cond_init(&P.cv, NULL);
 
     fmb_handle *h = NULL;
+    fmb_bind_thread_to_device_node(P.cfg.device); /* best effort: node-local pinned buffers */
     rc = fmb_create(&P.cfg, &h);
     if (rc != FMB_OK) { fprintf(stderr, "fmb_create: %s\n", fmb_last_error()); return 1; }
     P.pcm_pitch = ((size_t) fmb_max_out_count(h) + 7) & ~(size_t) 7;

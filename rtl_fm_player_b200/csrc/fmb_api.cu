@@ -6,9 +6,14 @@
  * rtl_fm_player.h:169) and demod_thread_fn (src/rtl_fm_player.c:855-933).
  * No CPU fallback: every compute entry point launches the CUDA kernels or fails.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <atomic>
+#include <cctype>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -547,6 +552,37 @@ int fmb_process(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t 
     int rc = fmb_submit(h, iq_host, iq_pitch, pcm_host, pcm_pitch, &ticket);
     if (rc != FMB_OK) return rc;
     return fmb_wait(h, ticket, n_out);
+}
+
+int fmb_bind_thread_to_device_node(int device)
+{
+    char bdf[32] = "", path[128], buf[4096];
+    CU(cudaDeviceGetPCIBusId(bdf, sizeof bdf, device));
+    for (char *p = bdf; *p; ++p) *p = (char) tolower((unsigned char) *p);
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return set_err(FMB_ERR_UNSUPPORTED, "NUMA node of the device is not exposed in sysfs");
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f || !fgets(buf, sizeof buf, f)) { if (f) fclose(f); return set_err(FMB_ERR_UNSUPPORTED, "cpulist of the NUMA node not readable"); }
+    fclose(f);
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return set_err(FMB_ERR_UNSUPPORTED, "sched_getaffinity");
+    int n = 0;
+    for (char *p = buf; *p;) { /* "0-15,32-47" */
+        while (*p && !isdigit((unsigned char) *p)) ++p;
+        if (!*p) break;
+        long a = strtol(p, &p, 10), b = a;
+        if (*p == '-') b = strtol(p + 1, &p, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET((int) c, &allowed)) { CPU_SET((int) c, &want); ++n; }
+    }
+    if (n == 0) return set_err(FMB_ERR_UNSUPPORTED, "no allowed CPU on the device's NUMA node");
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return set_err(FMB_ERR_UNSUPPORTED, "sched_setaffinity");
+    return node;
 }
 
 int fmb_host_alloc(void **ptr, size_t bytes)
