@@ -75,5 +75,6 @@ int fmb_design_tables(const fmb_config *cfg, fmb_tables *t)
         if (cfg->deemph != 0.0 && cfg->deemph_lambda > 0.0f) t->lambda = cfg->deemph_lambda;
     }
     t->pcm_scale = cfg->volume * 32768.0f; /* :717 */
+    t->one = 1.0f;
     return FMB_OK;
 }

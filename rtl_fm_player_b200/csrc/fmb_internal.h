@@ -26,6 +26,9 @@ typedef struct fmb_tables {
     float swf, cwf;        /* sin/cos of 2*pi*19000/rate_in (:421-423)                           */
     float lambda;          /* de-emphasis pole (:1577)                                           */
     float pcm_scale;       /* volume * 32768 (:717)                                              */
+    float one;             /* 1.0f, opaque to the compiler: acc = fma(product, one, acc) is the exactly
+                              rounded acc + product as ONE packed FFMA2; a literal 1.0 would let ptxas
+                              fold it back into add.f32x2 and contract that with the multiply         */
 } fmb_tables;
 
 /* Host-side design with glibc sinf/cosf/exp, the reference's float expressions. */
