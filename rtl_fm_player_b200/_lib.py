@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfmb.so")
+LIB_PATH = os.environ.get("FMB_LIB_PATH") or os.path.join(_HERE, "libfmb.so")   # FMB_LIB_PATH: a tuning build, tools/ only
 
 FMB_OK = 0
 FMB_ERR_ARG, FMB_ERR_UNSUPPORTED, FMB_ERR_CUDA, FMB_ERR_NOMEM, FMB_ERR_STATE, FMB_ERR_IO = -1, -2, -3, -4, -5, -6

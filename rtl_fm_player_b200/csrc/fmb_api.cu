@@ -62,6 +62,12 @@ struct fmb_handle {
     fmb_tables tab;
     int n_dem;                 /* demodulated samples per stream per step */
     int grid;                  /* CTAs of the demod kernel */
+    int ctas_per_sm = 0;       /* > 0 when the grid is exactly one full wave (SMs x occupancy) */
+    int stagger = 0;           /* clocks between the starts of the CTAs sharing an SM (see fmb_kparams) */
+    unsigned int *d_sm_slots = nullptr;
+    int chunk = 0, n_whole = 0; /* dynamic work assignment of the demod kernel (0 = static), see fmb_kparams */
+    unsigned int *d_tickets = nullptr;
+    unsigned int ticket_base = 0;
     int max_out;
     /* resampler bookkeeping (common to all streams) */
     int phase;                 /* prev_lpr_index */
@@ -217,6 +223,17 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
         kp.slow = 1; kp.fast = 1; kp.phase0 = 0; kp.dec = 1; kp.dec_c0 = 0;
     }
     kp.quirk = quirk ? 1 : 0;
+    kp.stagger = h->ctas_per_sm > 1 ? h->stagger : 0;
+    kp.ctas_per_sm = h->ctas_per_sm;
+    kp.sm_slots = h->d_sm_slots;
+    if (h->chunk > 0) {
+        const int spb = h->n_dem / FMB_NSUB;
+        kp.chunk = h->chunk;
+        kp.n_whole = h->n_whole;
+        kp.tickets = h->d_tickets;
+        kp.ticket_base = h->ticket_base;
+        h->ticket_base += (unsigned int) (h->n_whole + (c.n_streams - h->n_whole) * (spb / h->chunk) + h->grid);
+    }
 
     fmb_config kc = c;
     if (c.rate_out2 <= 0) kc.mode = 0;
@@ -246,7 +263,11 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     dp.pcm_scale = h->tab.pcm_scale;
     dp.fallbacks = h->d_fallbacks;
     if (prof) CU(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
+#ifdef FMB_TUNE_SKIP_DEEMPH   /* tools/build_variant.sh only: timing experiment, PCM is not produced */
+    e = cudaSuccess;
+#else
     e = (cudaError_t) fmb_launch_deemph(&dp, h->s_aux);
+#endif
     if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_deemph_kernel launch", e);
     g_launches++;
     if (prof) { CU(cudaEventRecord(h->pev[1][1][h->pcount[1]], h->s_aux)); h->pcount[1]++; }
@@ -360,6 +381,7 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
             }
             const long long slots = (long long) occ * sms;
             h->grid = (int) (units < slots ? units : slots);
+            if (units >= slots) h->ctas_per_sm = occ;
         }
     }
     h->phase = 0;
@@ -391,6 +413,26 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
     CUH(cudaMalloc(&h->d_fallbacks, sizeof(unsigned int)));
     CUH(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned int)));
+    CUH(cudaMalloc(&h->d_sm_slots, sizeof(unsigned int) * 1024));
+    CUH(cudaMemset(h->d_sm_slots, 0, sizeof(unsigned int) * 1024));
+    CUH(cudaMalloc(&h->d_tickets, sizeof(unsigned int)));
+    CUH(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
+    {
+        const char *ev = getenv("FMB_STAGGER");
+        h->stagger = ev ? atoi(ev) : FMB_DEFAULT_STAGGER;
+        /* Dynamic work assignment when the grid is one full resident wave: the first streams are handed
+         * out whole, the last FMB_TAIL_PCT percent in chunks of FMB_CHUNK sub-tiles (tuning knobs;
+         * defaults measured, profiles/).  FMB_CHUNK=0 keeps the static split. */
+        const int spb = h->n_dem / FMB_NSUB;
+        const char *ec = getenv("FMB_CHUNK"), *et = getenv("FMB_TAIL_PCT");
+        int chunk = ec ? atoi(ec) : FMB_DEFAULT_CHUNK, tail = et ? atoi(et) : FMB_DEFAULT_TAIL_PCT;
+        if (tail < 0) tail = 0;
+        if (tail > 100) tail = 100;
+        if (h->ctas_per_sm > 0 && chunk > 0 && chunk <= spb && spb % chunk == 0) {
+            h->chunk = chunk;
+            h->n_whole = (int) ((long long) cfg->n_streams * (100 - tail) / 100);
+        }
+    }
     {
         /* the de-emphasis pass runs beside the NEXT step's demod kernel: give it the highest priority
          * so its few CTAs take the first SM slots that free up instead of queueing behind that grid */
@@ -421,6 +463,8 @@ int fmb_destroy(fmb_handle *h)
     }
     if (h->d_de_state) cudaFree(h->d_de_state);
     if (h->d_fallbacks) cudaFree(h->d_fallbacks);
+    if (h->d_sm_slots) cudaFree(h->d_sm_slots);
+    if (h->d_tickets) cudaFree(h->d_tickets);
     if (h->d_dem) cudaFree(h->d_dem);
     for (auto &s : h->slot) {
         if (s.d_iq) cudaFree(s.d_iq);

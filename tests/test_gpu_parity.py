@@ -219,6 +219,25 @@ def test_config_4_maximum_size_8192_streams_on_one_gpu():
     assert (sums == sums[0]).all()
 
 
+@pytest.mark.parametrize("cfgname,kind,chunk,tail", [("stereo192", "fm_stereo", 1, 100), ("stereo192", "random", 4, 50),
+                                                     ("mono192", "fm_mono", 2, 100), ("mono192", "fm_mono", 8, 100),
+                                                     ("stereo240", "fm_stereo", 2, 60), ("stereo192", "fm_stereo", 0, 0)])
+def test_dynamic_work_assignment_does_not_change_the_result(monkeypatch, cfgname, kind, chunk, tail):
+    """A batch that fills the GPU (>= SMs x resident CTAs work units) is handed out through the ticket
+    counter: whole streams first, then chunks of `chunk` sub-tiles that re-enter a stream through the
+    recomputed lead-in.  Every split must give the oracle's PCM, over several carried blocks."""
+    monkeypatch.setenv("FMB_CHUNK", str(chunk))
+    monkeypatch.setenv("FMB_TAIL_PCT", str(tail))
+    n, uniq, blocks = 64, 8, 3
+    c = CONFIGS[cfgname]
+    iq = R.synth.batch(kind, n, c["rate_in"], c.get("offset_tuning", 0), blocks * B // 2, unique=uniq)
+    with R.FmBatch(cfg_for(cfgname, n_streams=n)) as fb:
+        pcm = fb.run(iq)
+    for s in range(uniq):
+        assert np.array_equal(pcm[s], PortOracle(**c).run(iq[s])), s
+    assert np.array_equal(pcm.reshape(n // uniq, uniq, -1), np.broadcast_to(pcm[:uniq], (n // uniq, uniq, pcm.shape[1])))
+
+
 def test_kernels_really_launch_and_errors_are_loud():
     iq = make_input("stereo192", "fm_stereo", 0, 1)[None, :]
     before = R.launch_count()
