@@ -438,7 +438,8 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
          * so its few CTAs take the first SM slots that free up instead of queueing behind that grid */
         int prio_lo = 0, prio_hi = 0;
         CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUH(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, prio_hi));
+        const char *ep = getenv("FMB_AUX_PRIO");   /* tuning knob: 0 = lowest (default-stream) priority */
+        CUH(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, (ep && atoi(ep) == 0) ? prio_lo : prio_hi));
     }
     CUH(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
     CUH(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));

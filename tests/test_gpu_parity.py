@@ -305,3 +305,17 @@ def test_unaligned_pcm_pitch(pitch_extra):
     got = np.concatenate(got, axis=1)
     for s in range(n):
         assert np.array_equal(got[s], want[s])
+
+
+def test_whole_stream_runs_on_random_bytes(monkeypatch):
+    """Dynamic assignment, every stream handed out whole (8 consecutive sub-tiles per CTA, the carried
+    sub-tile state chained through shared memory), on uniform-random bytes (every atan2 branch)."""
+    monkeypatch.setenv("FMB_CHUNK", "8")
+    monkeypatch.setenv("FMB_TAIL_PCT", "0")
+    n, uniq, blocks = 64, 4, 2
+    iq = np.stack([make_input("stereo192", "random", s % uniq, blocks) for s in range(n)])
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        pcm = fb.run(iq)
+    want = [PortOracle(**CONFIGS["stereo192"]).run(iq[s]) for s in range(uniq)]
+    for s in range(n):
+        assert np.array_equal(pcm[s], want[s % uniq]), s
