@@ -16,4 +16,15 @@ for kw, kind in ((dict(rate_in=240000, rate_out2=48000, mode=2, size=90), "rando
         pcm = fb.run(iq)
     for s in range(n):
         assert np.array_equal(pcm[s], PortOracle(**kw).run(iq[s])), (kw, s)
+# the dynamic work assignment (a batch that fills the GPU): whole-stream runs chained through shared memory,
+# fine-grain runs with lead-ins, the named-barrier hand-overs, on random bytes
+os.environ["FMB_CHUNK"], os.environ["FMB_TAIL_PCT"] = "2", "30"
+kw = dict(rate_in=192000, rate_out2=48000, mode=2, size=90)
+n, uniq = 60, 3
+iq = np.stack([R.synth.capture("random", s % uniq, 192000, 0, B // 2) for s in range(n)])
+with R.FmBatch(R.DemodConfig(n_streams=n, **kw)) as fb:
+    pcm = fb.run(iq)
+want = [PortOracle(**kw).run(iq[s]) for s in range(uniq)]
+for s in range(n):
+    assert np.array_equal(pcm[s], want[s % uniq]), ("dynamic", s)
 print("sanitize case ok")
