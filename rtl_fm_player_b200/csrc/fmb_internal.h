@@ -35,7 +35,9 @@ typedef struct fmb_tables {
 int fmb_design_tables(const fmb_config *cfg, fmb_tables *t);
 
 /* Kernel geometry (see DESIGN.md "Kernel 1"). */
+#ifndef FMB_NT
 #define FMB_NT 256                 /* threads per CTA                                   */
+#endif
 #define FMB_RUN 8                  /* consecutive demodulated samples per thread         */
 #define FMB_NSUB (FMB_NT * FMB_RUN)/* demodulated samples per sub-tile (2048)            */
 #define FMB_DEFAULT_CHUNK 2        /* sub-tiles per fine-grain run, 0 = static split (env FMB_CHUNK)   */

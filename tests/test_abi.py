@@ -27,7 +27,7 @@ def declared_symbols():
         src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src):
             n = m.group(1)
-            if n.startswith(("fmb_", "filesrc_", "fm_wav_", "fm_dropin_")) or n in DROPIN:
+            if n.startswith(("fmb_", "filesrc_", "fm_wav_", "fm_timeshift_", "fm_dropin_")) or n in DROPIN:
                 names.add(n)
     return sorted(names)
 

@@ -249,3 +249,79 @@ def test_dropin_layout_header_is_fresh():
 
 # sha256 of the reference's 260-byte headers, from oracle/_ref/libfmref.so:ref_wav_header in the authoring container
 GOLDEN_WAV = {'header_2': '37c5c07cffccd6f94a63c0cc58d6ce6e98f085193e2fbdf3a7b5ba2dba5ea48c', 'header_1': '7f3cfa10a8d1dff5fc794db3df826e2f92086088e2bd7df21d592acc46f87773'}
+
+
+# ------------------------------------------------------------------------------------------
+# timeshift ring (include/fm_timeshift.h) against a restatement of output_thread_fn's slot
+# arithmetic, reference src/rtl_fm_player.c:962-1010
+# ------------------------------------------------------------------------------------------
+class RefTimeshift:
+    """circbufferbotton / circbufferfull / circbufferout exactly as :945-1010 keeps them (one channel)."""
+
+    def __init__(self, slots):
+        self.slots, self.bottom, self.full, self.ring = slots, 0, 0, {}
+
+    def push(self, cluster, shift):
+        self.ring[self.bottom] = cluster                      # :964
+        if shift < 0:                                         # :982
+            shift = 0
+        if self.full == 0:                                    # :985-987
+            if shift > self.bottom:
+                shift = self.bottom
+        elif shift > self.slots - 2:                          # :988-991
+            shift = self.slots - 2
+        out = self.bottom - shift                             # :994
+        if out < 0:                                           # :995-997
+            out = self.slots - (shift - self.bottom)
+        played = self.ring[out]                               # :1000 / :1004
+        self.bottom += 1                                      # :1007-1010
+        if self.bottom >= self.slots:
+            self.full, self.bottom = 1, 0
+        return out, shift, played
+
+
+def _ts_lib():
+    L = C.CDLL(R.LIB_PATH)
+    L.fm_timeshift_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.fm_timeshift_destroy.argtypes = [C.c_void_p]
+    L.fm_timeshift_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]
+    L.fm_timeshift_playback.argtypes = [C.c_void_p, C.c_int]
+    L.fm_timeshift_playback.restype = C.c_void_p
+    L.fm_timeshift_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fm_timeshift_slots_for_kbytes.argtypes = [C.c_long]
+    return L
+
+
+def test_timeshift_slot_count_is_the_players():
+    L = _ts_lib()
+    assert L.fm_timeshift_slots_for_kbytes(180 * 1024) == 5760     # 180 MiB default, :1363-1364
+    assert L.fm_timeshift_slots_for_kbytes(100) == 3
+    ts = C.c_void_p()
+    assert L.fm_timeshift_create(C.byref(ts), 1, 1) == -1 and L.fm_timeshift_create(C.byref(ts), 4, 0) == -1
+
+
+@pytest.mark.parametrize("slots,n_streams", [(5, 1), (7, 3)])
+def test_timeshift_ring_plays_what_the_reference_would(slots, n_streams):
+    L = _ts_lib()
+    CL = 32768
+    rng = np.random.default_rng(slots)
+    ts = C.c_void_p()
+    assert L.fm_timeshift_create(C.byref(ts), slots, n_streams) == 0
+    refs = [RefTimeshift(slots) for _ in range(n_streams)]
+    shifts = [0, 0, 1, 3, 9, -2, 2, 2, 2, 100, 100, 0, 1, 4, 6, 5, 0, 3, 3, 3, 3, 3, 1]   # keyboard A/D/L walks
+    out = np.empty((n_streams, CL), dtype=np.uint8)
+    pitch = CL + 64                                                                       # padded producer rows
+    for step, want_shift in enumerate(shifts):
+        batch = rng.integers(0, 256, size=(n_streams, pitch), dtype=np.uint8)
+        sh = C.c_int(want_shift)
+        slot = L.fm_timeshift_push(ts, batch.ctypes.data, pitch, C.byref(sh), out.ctypes.data)
+        for s in range(n_streams):
+            r_out, r_shift, played = refs[s].push(batch[s, :CL].copy(), want_shift)
+            assert (slot, sh.value) == (r_out, r_shift), (step, s)
+            assert np.array_equal(out[s], played), (step, s)
+            p = L.fm_timeshift_playback(ts, s)
+            assert np.array_equal(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (CL,)), played)
+        b, w, n = C.c_int(), C.c_int(), C.c_int()
+        assert L.fm_timeshift_state(ts, C.byref(b), C.byref(w), C.byref(n)) == 0
+        assert (b.value, w.value, n.value) == (refs[0].bottom, refs[0].full, slots)
+    L.fm_timeshift_destroy(ts)
