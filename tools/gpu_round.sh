@@ -17,9 +17,11 @@ cat gpurun_out/${TAG}_bench_mono.json
 timeout 300 python bench.py --steps 20 --warmup 3 --precision fma --no-cpu > gpurun_out/${TAG}_bench_fma.json 2>> gpurun_out/${TAG}_bench.err
 cat gpurun_out/${TAG}_bench_fma.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
-   python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
+   python bench.py --steps 4 --warmup 3 --no-cpu --no-fma-alt > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fmb_demod -s 3 -c 2 -f -o gpurun_out/${TAG}_demod \
-   python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+   python bench.py --steps 3 --warmup 3 --no-cpu --no-fma-alt > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmb_demod -s 3 -c 1 -f -o gpurun_out/${TAG}_demod_mono \
+   python bench.py --steps 3 --warmup 3 --no-cpu --no-fma-alt --mode mono >> gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmb_deemph -s 3 -c 1 -f -o gpurun_out/${TAG}_deemph \
-   python bench.py --steps 3 --warmup 3 --no-cpu >> gpurun_out/${TAG}_ncu_full.log 2>&1
+   python bench.py --steps 3 --warmup 3 --no-cpu --no-fma-alt >> gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out
