@@ -241,7 +241,12 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        backend = os.environ.get("FMB_BENCH_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    red_dev = "cuda" if dist is None or dist.get_backend() == "nccl" else "cpu"
 
     S, K, W = args.streams, max(1, args.steps), max(3, args.warmup)
     stereo = args.mode == "stereo"
@@ -255,7 +260,7 @@ def run_ours(args):
     # synthetic input: `unique` distinct channels per rank (global stream ids), replicated to S;
     # nbuf consecutive blocks of each so that successive steps read different HBM
     uniq = min(args.unique, S)
-    base = rank * S
+    base = int(os.environ.get("FMB_BENCH_DATA_RANK", rank)) * S     # (override: time another rank's channels on one GPU)
     kind = "fm_stereo" if stereo else "fm_mono"
     host = np.empty((args.nbuf, S, BLOCK), dtype=np.uint8)
     from concurrent.futures import ThreadPoolExecutor
@@ -269,6 +274,9 @@ def run_ours(args):
         host[:, s] = host[:, s % uniq]
     dev_in = [torch.from_numpy(host[b]).cuda() for b in range(args.nbuf)]
     dev_pcm = torch.empty((S, pitch), dtype=torch.int16, device="cuda")
+    if os.environ.get("FMB_BENCH_SIDE_STREAM"):                       # experiment: not the legacy default stream
+        _side = torch.cuda.Stream()
+        torch.cuda.set_stream(_side)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(i):
@@ -291,8 +299,10 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
+        t_host = time.perf_counter()
         for i in range(K):
             step(W + i)
+        t_host = time.perf_counter() - t_host       # host time to enqueue the K steps (must stay below the device time)
         fb.join(stream)
         e1.record()
         barrier()
@@ -301,7 +311,7 @@ def run_ours(args):
     prof = fb.profile_read()
     fb.profile_enable(False)
     if dist is not None:
-        t = torch.tensor([ms_total], device="cuda")
+        t = torch.tensor([ms_total], device=red_dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     samples_step_all = S * SAMPLES_PER_BLOCK * world
@@ -325,7 +335,7 @@ def run_ours(args):
         barrier()
         fma_ms = f0.elapsed_time(f1)
         if dist is not None:
-            t = torch.tensor([fma_ms], device="cuda")
+            t = torch.tensor([fma_ms], device=red_dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             fma_ms = float(t.item())
         fma_alt = {"value": samples_step_all * K / (fma_ms * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": fma_ms / K,
@@ -354,7 +364,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda")
+        t = torch.tensor([e2e_s], device=red_dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = samples_step_all * K / e2e_s * 1e-6
@@ -386,7 +396,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": S * n_out * 2 * world, "ms_per_step": e2e_s / K * 1e3,
                 "api": "fmb_submit/fmb_wait, pinned host buffers, 2 steps in flight", "pcm_checksum": checksum,
                 "host_numa_node": numa_node},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": t_host / K * 1e3,
         "roofline": {"bound": "hbm", "kernel": "fmb_demod_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "alg_bytes_per_launch": alg, "peak_source": peak_src,

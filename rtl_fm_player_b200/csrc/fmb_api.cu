@@ -27,6 +27,8 @@ static_assert(offsetof(fmb_stream_state, raw_tail) % 16 == 0 && sizeof(fmb_strea
 
 namespace {
 
+constexpr int kLrBufs = 3;
+
 thread_local char g_err[512] = "";
 std::atomic<long> g_launches{0};
 
@@ -77,7 +79,10 @@ struct fmb_handle {
     int state_cur = 0;
     float *d_de_state = nullptr;     /* [n_streams][2] */
     unsigned int *d_fallbacks = nullptr; /* de-emphasis chunks redone sequentially (diagnostic) */
-    float *d_lr[2] = {nullptr, nullptr};
+    /* decoder output, kLrBufs deep: the de-emphasis pass of step b reads buffer b%3 while the demod kernels of
+     * steps b+1 and b+2 write the other two, so a de-emphasis pass that only gets SM slots when the next demod
+     * kernel drains (its CTAs are resident for the whole launch) is never waited for by the one after */
+    float *d_lr[kLrBufs] = {};
     long long lr_pitch = 0;
     int lr_cur = 0;
     float *d_dem = nullptr;          /* debug tap */
@@ -85,8 +90,8 @@ struct fmb_handle {
     int last_n_out = 0, last_lr = 0;
     /* streams / events */
     cudaStream_t s_aux = nullptr, s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_demod[2] = {nullptr, nullptr}, ev_deemph[2] = {nullptr, nullptr};
-    bool deemph_pending[2] = {false, false};
+    cudaEvent_t ev_demod[kLrBufs] = {}, ev_deemph[kLrBufs] = {};
+    bool deemph_pending[kLrBufs] = {};
     cudaEvent_t ev_fork = nullptr;
     /* pipelined host path */
     Slot slot[FMB_PIPE_DEPTH];
@@ -276,7 +281,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
 
     h->last_n_out = n_out;
     h->last_lr = b;
-    h->lr_cur ^= 1;
+    h->lr_cur = (h->lr_cur + 1) % kLrBufs;
     h->state_cur ^= 1;
     h->phase = next_phase(h, h->phase);
     h->blocks_done++;
@@ -404,6 +409,8 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     for (int i = 0; i < 2; ++i) {
         CUH(cudaMalloc(&h->d_state[i], st_bytes));
         CUH(cudaMemset(h->d_state[i], 0, st_bytes));
+    }
+    for (int i = 0; i < kLrBufs; ++i) {
         CUH(cudaMalloc(&h->d_lr[i], (size_t) h->lr_pitch * cfg->n_streams * sizeof(float)));
         CUH(cudaMemset(h->d_lr[i], 0, (size_t) h->lr_pitch * cfg->n_streams * sizeof(float)));
         CUH(cudaEventCreateWithFlags(&h->ev_demod[i], cudaEventDisableTiming));
@@ -456,8 +463,9 @@ int fmb_destroy(fmb_handle *h)
     if (!h) return FMB_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i)
         if (h->d_state[i]) cudaFree(h->d_state[i]);
+    for (int i = 0; i < kLrBufs; ++i) {
         if (h->d_lr[i]) cudaFree(h->d_lr[i]);
         if (h->ev_demod[i]) cudaEventDestroy(h->ev_demod[i]);
         if (h->ev_deemph[i]) cudaEventDestroy(h->ev_deemph[i]);
@@ -503,7 +511,7 @@ int fmb_reset(fmb_handle *h)
     CU(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) h->cfg.n_streams));
     h->phase = 0;
     h->blocks_done = 0;
-    h->deemph_pending[0] = h->deemph_pending[1] = false;
+    for (bool &pend : h->deemph_pending) pend = false;
     for (auto &s : h->slot) s.busy = false;
     return FMB_OK;
 }
@@ -522,7 +530,7 @@ int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, in
 int fmb_join(fmb_handle *h, void *stream)
 {
     if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < kLrBufs; ++b)
         if (h->deemph_pending[b]) CU(cudaStreamWaitEvent((cudaStream_t) stream, h->ev_deemph[b], 0));
     return FMB_OK;
 }
