@@ -274,9 +274,6 @@ def run_ours(args):
         host[:, s] = host[:, s % uniq]
     dev_in = [torch.from_numpy(host[b]).cuda() for b in range(args.nbuf)]
     dev_pcm = torch.empty((S, pitch), dtype=torch.int16, device="cuda")
-    if os.environ.get("FMB_BENCH_SIDE_STREAM"):                       # experiment: not the legacy default stream
-        _side = torch.cuda.Stream()
-        torch.cuda.set_stream(_side)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(i):
