@@ -65,8 +65,6 @@ struct fmb_handle {
     int n_dem;                 /* demodulated samples per stream per step */
     int grid;                  /* CTAs of the demod kernel */
     int ctas_per_sm = 0;       /* > 0 when the grid is exactly one full wave (SMs x occupancy) */
-    int stagger = 0;           /* clocks between the starts of the CTAs sharing an SM (see fmb_kparams) */
-    unsigned int *d_sm_slots = nullptr;
     int chunk = 0, n_whole = 0; /* dynamic work assignment of the demod kernel (0 = static), see fmb_kparams */
     unsigned int *d_tickets = nullptr;
     unsigned int ticket_base = 0;
@@ -228,9 +226,6 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
         kp.slow = 1; kp.fast = 1; kp.phase0 = 0; kp.dec = 1; kp.dec_c0 = 0;
     }
     kp.quirk = quirk ? 1 : 0;
-    kp.stagger = h->ctas_per_sm > 1 ? h->stagger : 0;
-    kp.ctas_per_sm = h->ctas_per_sm;
-    kp.sm_slots = h->d_sm_slots;
     if (h->chunk > 0) {
         const int spb = h->n_dem / FMB_NSUB;
         kp.chunk = h->chunk;
@@ -420,13 +415,9 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
     CUH(cudaMalloc(&h->d_fallbacks, sizeof(unsigned int)));
     CUH(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned int)));
-    CUH(cudaMalloc(&h->d_sm_slots, sizeof(unsigned int) * 1024));
-    CUH(cudaMemset(h->d_sm_slots, 0, sizeof(unsigned int) * 1024));
     CUH(cudaMalloc(&h->d_tickets, sizeof(unsigned int)));
     CUH(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
     {
-        const char *ev = getenv("FMB_STAGGER");
-        h->stagger = ev ? atoi(ev) : FMB_DEFAULT_STAGGER;
         /* Dynamic work assignment when the grid is one full resident wave: the first streams are handed
          * out whole, the last FMB_TAIL_PCT percent in chunks of FMB_CHUNK sub-tiles (tuning knobs;
          * defaults measured, profiles/).  FMB_CHUNK=0 keeps the static split. */
@@ -445,8 +436,7 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
          * so its few CTAs take the first SM slots that free up instead of queueing behind that grid */
         int prio_lo = 0, prio_hi = 0;
         CUH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        const char *ep = getenv("FMB_AUX_PRIO");   /* tuning knob: 0 = lowest (default-stream) priority */
-        CUH(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, (ep && atoi(ep) == 0) ? prio_lo : prio_hi));
+        CUH(cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, prio_hi));
     }
     CUH(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
     CUH(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -472,7 +462,6 @@ int fmb_destroy(fmb_handle *h)
     }
     if (h->d_de_state) cudaFree(h->d_de_state);
     if (h->d_fallbacks) cudaFree(h->d_fallbacks);
-    if (h->d_sm_slots) cudaFree(h->d_sm_slots);
     if (h->d_tickets) cudaFree(h->d_tickets);
     if (h->d_dem) cudaFree(h->d_dem);
     for (auto &s : h->slot) {

@@ -42,7 +42,6 @@ int fmb_design_tables(const fmb_config *cfg, fmb_tables *t);
 #define FMB_NSUB (FMB_NT * FMB_RUN)/* demodulated samples per sub-tile (2048)            */
 #define FMB_DEFAULT_CHUNK 2        /* sub-tiles per fine-grain run, 0 = static split (env FMB_CHUNK)   */
 #define FMB_DEFAULT_TAIL_PCT 20   /* percent of the streams handed out in fine-grain runs (env FMB_TAIL_PCT) */
-#define FMB_DEFAULT_STAGGER 0      /* clocks; see fmb_kparams.stagger (env FMB_STAGGER overrides) */
 #define FMB_WARM 256               /* recomputed lead-in of a segment that is not first  */
 
 typedef struct fmb_kparams {
@@ -61,13 +60,6 @@ typedef struct fmb_kparams {
     int dec;                       /* fast/slow when integral, else 0                     */
     int dec_c0;                    /* tick at relative i  <=>  (i + dec_c0) % dec == dec-1 */
     int quirk;                     /* patch d[1] with R of the tick at i=0   */
-    /* Phase stagger of the CTAs that share an SM (0 = off): the k-th CTA to arrive on an SM
-     * (counted in sm_slots[%smid], modulo ctas_per_sm) starts k*stagger clocks late, so that
-     * the FMA-bound stage of one CTA overlaps the ALU/issue-bound stages of its neighbours
-     * instead of all resident CTAs marching through the same stage together. */
-    int stagger;
-    int ctas_per_sm;
-    unsigned int *sm_slots;
     /* Dynamic work assignment (chunk > 0): see "work assignment" in fmb_demod_kernel. */
     int chunk;                     /* units per fine-grain run; divides n_dem / FMB_NSUB  */
     int n_whole;                   /* streams handed out whole before the fine-grain runs */
