@@ -84,8 +84,9 @@ int fmb_preset_mono_192k(fmb_config *cfg);
 
 /* Tuning (read once here from the environment; results never depend on it): FMB_CHUNK = sub-tiles
  * (2048 demodulated samples) per fine-grain run of the demod kernel's dynamic work assignment, 0 = static
- * split, default 2; FMB_TAIL_PCT = percent of the streams handed out in such runs instead of whole,
- * default 20.  See DESIGN.md "Kernel 1". */
+ * split, default 2; FMB_TAIL_PCT = percent of the streams handed out in such runs instead of whole
+ * (default: about two such runs per CTA, for batches of at least two streams per CTA; smaller batches use
+ * the static split).  See DESIGN.md "Kernel 1". */
 int fmb_create(const fmb_config *cfg, fmb_handle **out);
 int fmb_destroy(fmb_handle *h);
 

@@ -418,17 +418,30 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     CUH(cudaMalloc(&h->d_tickets, sizeof(unsigned int)));
     CUH(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
     {
-        /* Dynamic work assignment when the grid is one full resident wave: the first streams are handed
-         * out whole, the last FMB_TAIL_PCT percent in chunks of FMB_CHUNK sub-tiles (tuning knobs;
-         * defaults measured, profiles/).  FMB_CHUNK=0 keeps the static split. */
+        /* Dynamic work assignment (see fmb_demod_kernel).  It pays when every CTA of the resident wave has
+         * several streams' worth of work: whole streams first, and about FMB_DEFAULT_TAIL_RUNS fine-grain
+         * runs of FMB_CHUNK sub-tiles per CTA at the end of the launch, so that the CTAs finish together.
+         * Smaller batches (64 streams on 444 CTAs) keep the static split into equal runs: a whole stream
+         * would be several CTAs' share.  FMB_CHUNK / FMB_TAIL_PCT (percent of the streams handed out in
+         * fine-grain runs) override the policy, for tuning and tests; FMB_CHUNK=0 forces the static split. */
         const int spb = h->n_dem / FMB_NSUB;
+        const long long units = (long long) cfg->n_streams * spb;
         const char *ec = getenv("FMB_CHUNK"), *et = getenv("FMB_TAIL_PCT");
-        int chunk = ec ? atoi(ec) : FMB_DEFAULT_CHUNK, tail = et ? atoi(et) : FMB_DEFAULT_TAIL_PCT;
-        if (tail < 0) tail = 0;
-        if (tail > 100) tail = 100;
-        if (h->ctas_per_sm > 0 && chunk > 0 && chunk <= spb && spb % chunk == 0) {
+        const int chunk = ec ? atoi(ec) : FMB_DEFAULT_CHUNK;
+        const bool forced = ec || et;
+        if (h->ctas_per_sm > 0 && chunk > 0 && chunk <= spb && spb % chunk == 0 &&
+            (forced || units >= 2LL * spb * h->grid)) {
+            int tail_streams;
+            if (et) {
+                int tail = atoi(et);
+                tail = tail < 0 ? 0 : tail > 100 ? 100 : tail;
+                tail_streams = cfg->n_streams - (int) ((long long) cfg->n_streams * (100 - tail) / 100);
+            } else {
+                tail_streams = (FMB_DEFAULT_TAIL_RUNS * chunk * h->grid + spb - 1) / spb;
+                if (tail_streams > cfg->n_streams) tail_streams = cfg->n_streams;
+            }
             h->chunk = chunk;
-            h->n_whole = (int) ((long long) cfg->n_streams * (100 - tail) / 100);
+            h->n_whole = cfg->n_streams - tail_streams;
         }
     }
     {

@@ -41,7 +41,7 @@ int fmb_design_tables(const fmb_config *cfg, fmb_tables *t);
 #define FMB_RUN 8                  /* consecutive demodulated samples per thread         */
 #define FMB_NSUB (FMB_NT * FMB_RUN)/* demodulated samples per sub-tile (2048)            */
 #define FMB_DEFAULT_CHUNK 2        /* sub-tiles per fine-grain run, 0 = static split (env FMB_CHUNK)   */
-#define FMB_DEFAULT_TAIL_PCT 20   /* percent of the streams handed out in fine-grain runs (env FMB_TAIL_PCT) */
+#define FMB_DEFAULT_TAIL_RUNS 2    /* fine-grain runs per CTA at the end of a launch (env FMB_TAIL_PCT overrides) */
 #define FMB_WARM 256               /* recomputed lead-in of a segment that is not first  */
 
 typedef struct fmb_kparams {

@@ -7,7 +7,8 @@ import numpy as np, torch
 import rtl_fm_player_b200 as R
 
 knob, mode, vals = sys.argv[1], sys.argv[2], sys.argv[3:]
-S, BLOCK, NBUF, K, W = 1024, R.FMB_REF_BLOCK_BYTES, 4, 20, 4
+S, BLOCK, NBUF, K, W = int(os.environ.get("SWEEP_STREAMS", "1024")), R.FMB_REF_BLOCK_BYTES, 4, 20, 4
+NBUF = max(1, min(NBUF, (6 << 30) // (S * BLOCK)))        # keep the inputs under 6 GiB
 stereo = mode == "stereo"
 uniq = 16
 host = np.empty((NBUF, S, BLOCK), dtype=np.uint8)
