@@ -143,6 +143,10 @@ int fmb_bind_thread_to_device_node(int device);
 
 /* Pinned host memory without CUDA headers. */
 int fmb_host_alloc(void **ptr, size_t bytes);
+/* The same, write-combined: for IQ upload buffers the CPU only ever WRITES (sequentially) and the GPU reads
+ * over PCIe without snooping the CPU caches.  Never for PCM buffers (CPU reads of write-combined memory
+ * are very slow).  Free with fmb_host_free. */
+int fmb_host_alloc_wc(void **ptr, size_t bytes);
 int fmb_host_free(void *ptr);
 
 /*

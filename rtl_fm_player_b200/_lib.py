@@ -74,6 +74,7 @@ SIGNATURES = {
     "fmb_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "fmb_bind_thread_to_device_node": (C.c_int, [C.c_int]),
     "fmb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "fmb_host_alloc_wc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "fmb_host_free": (C.c_int, [C.c_void_p]),
     "fmb_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FmbStreamState), C.POINTER(C.c_int),
                                 C.POINTER(C.c_uint64)]),

@@ -647,6 +647,13 @@ int fmb_host_alloc(void **ptr, size_t bytes)
     return FMB_OK;
 }
 
+int fmb_host_alloc_wc(void **ptr, size_t bytes)
+{
+    if (!ptr) return set_err(FMB_ERR_ARG, "NULL argument");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocWriteCombined));
+    return FMB_OK;
+}
+
 int fmb_host_free(void *ptr)
 {
     if (ptr) CU(cudaFreeHost(ptr));
