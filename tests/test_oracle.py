@@ -104,3 +104,38 @@ def test_quirk_matters_at_240k():
     b = PortOracle(inplace_quirk=0, **kw).run(iq)
     assert a.shape == b.shape and not np.array_equal(a, b)
     assert np.array_equal(a[:6552], b[:6552])      # block 0 has no tick on its first sample
+
+
+def test_closed_form_of_the_resampler_ticks_equals_the_reference_accumulator():
+    """The generic tick path of the demod kernel places output frame f0+m of a sub-tile that starts at
+    sample j0 on sample i = ((m+1)*fast - rem0 - 1) // slow, with phase0 + j0*slow = f0*fast + rem0
+    (rtl_fm_player_b200/csrc/fmb_kernels.cu).  The reference walks (prev_lpr_index += slow) >= fast
+    (src/rtl_fm_player.c:570-572).  Same ticks, same frame numbers, for any ratio and phase."""
+    rng = np.random.default_rng(7)
+    cases = [(48000, 240000, 0), (48000, 192000, 0), (44100, 250000, 0), (48000, 100000, 0), (1, 1, 0)]
+    for _ in range(40):
+        fast = int(rng.integers(2, 400000))
+        slow = int(rng.integers(1, fast))
+        cases.append((slow, fast, int(rng.integers(0, fast))))
+    for slow, fast, phase0 in cases:
+        n, sub = 16384, 2048
+        want, p, frame = {}, phase0, 0                      # the reference loop over one block
+        for i in range(n):
+            p += slow
+            if p >= fast:
+                p -= fast
+                want[frame] = i
+                frame += 1
+        got = {}
+        for j0 in range(0, n, sub):                         # the kernel's per-sub-tile closed form
+            a0 = phase0 + j0 * slow
+            f0, rem0 = divmod(a0, fast)
+            m = 0
+            while True:
+                i = ((m + 1) * fast - rem0 - 1) // slow
+                if i >= sub:
+                    break
+                assert f0 + m not in got
+                got[f0 + m] = j0 + i
+                m += 1
+        assert got == want, (slow, fast, phase0)
