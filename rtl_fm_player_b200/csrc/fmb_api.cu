@@ -338,6 +338,9 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     if (cfg->precision != FMB_PRECISION_EXACT && cfg->precision != FMB_PRECISION_FMA)
         return set_err(FMB_ERR_ARG, "bad precision");
     if (cfg->rate_out2 > cfg->rate_in) return set_err(FMB_ERR_UNSUPPORTED, "rate_out2 > rate_in");
+    /* the tick schedule of a sub-tile is evaluated in 32-bit arithmetic: (ticks + 1) * rate_in must fit */
+    if ((long long) (FMB_NSUB + FMB_NT + 2) * cfg->rate_in >= (1LL << 32))
+        return set_err(FMB_ERR_UNSUPPORTED, "rate_in too high (limit about 1.86 MHz after the /8 channel filter)");
     if (cfg->mode == 2 && cfg->rate_out2 > 0 && 2LL * cfg->rate_out2 > cfg->rate_in)
         return set_err(FMB_ERR_UNSUPPORTED, "stereo needs rate_in >= 2*rate_out2 (in-place output, reference :593-597)");
     {
