@@ -227,6 +227,114 @@ long ref_layout(int what)
     return -1;
 }
 
+/* ==========================================================================================
+ * The reference's own THREADS, offline.
+ *
+ * ref_player_run() does what main() does between option parsing and the key loop (:1382-1385,
+ * :1575-1578, :1601-1618, :1647-1665) and then lets the reference's dongle_thread_fn (:839),
+ * demod_thread_fn (:855) and output_thread_fn (:935) run until the capture file is exhausted; the WAV
+ * is written by the reference's InitWaveOut / output thread / CloseWaveOut.  librtlsdr is replaced by
+ * a capture-file source handed in as two function pointers with the rtlsdr_read_async /
+ * rtlsdr_cancel_async contract (the product's include/fm_filesrc.h; this file does not link it).
+ *
+ * The threads call rotate_90_u8_f32 / u8_f32 / full_demod (and this function the init_* trio) through
+ * the PLT of this shared object.  Loaded on its own, they bind to the reference's CPU code.  With
+ * rtl_fm_player_b200/libfmb.so loaded RTLD_GLOBAL first (what LD_PRELOAD does for the real player) they
+ * bind to the CUDA drop-in of include/fm_dropin.h -- the unmodified player, demodulating on the GPU.
+ * ========================================================================================== */
+typedef int (*ref_read_async_fn)(void *src, rtlsdr_read_async_cb_t cb, void *ctx, uint32_t buf_num, uint32_t buf_len);
+typedef int (*ref_cancel_async_fn)(void *src);
+static ref_read_async_fn g_src_read;
+static ref_cancel_async_fn g_src_cancel;
+static void *g_src;
+
+int rtlsdr_read_async(rtlsdr_dev_t *dev, rtlsdr_read_async_cb_t cb, void *ctx, uint32_t buf_num, uint32_t buf_len)
+{
+    (void) dev;
+    return g_src_read ? g_src_read(g_src, cb, ctx, buf_num, buf_len) : -1;
+}
+int rtlsdr_cancel_async(rtlsdr_dev_t *dev)
+{
+    (void) dev;
+    return g_src_cancel ? g_src_cancel(g_src) : 0;
+}
+int SDL_QueueAudio(SDL_AudioDeviceID dev, const void *data, uint32_t len) { (void) dev; (void) data; (void) len; return 0; }
+const char *SDL_GetError(void) { return ""; }
+
+/* address of the input ring's fill counter, for the file source's back-pressure (the ring overwrites on
+ * overrun, :821-834) */
+volatile uint32_t *ref_player_input_fill(uint32_t *fill_max)
+{
+    if (fill_max) *fill_max = _input_buffer_size_max;
+    return (volatile uint32_t *) &_input_buffer_size;
+}
+
+int ref_player_run(const struct ref_cfg *c, const char *wav_path, ref_read_async_fn read_async,
+                   ref_cancel_async_fn cancel_async, void *src)
+{
+    int spins;
+    g_src_read = read_async; g_src_cancel = cancel_async; g_src = src;
+    _do_exit = 0;
+    _input_buffer_rpos = _input_buffer_wpos = _input_buffer_size = 0;
+    _output_buffer_rpos = _output_buffer_wpos = _output_buffer_size = 0;
+    _circbufferslots = 8;                            /* main: 180 MiB (:1363-1364); 8 slots do for a file */
+    _circbuffeshift = 0;
+    _circbuffer = (char *) malloc((size_t) _circbufferslots * CIRCBUFFCLUSTER);
+    if (!_circbuffer) return -1;
+
+    dongle_init(&dongle);                            /* :1382-1385 */
+    demod_init(&demod);
+    output_init(&output);
+    controller_init(&controller);
+    demod.rate_in = c->rate_in;                      /* the flags that change numerics, as ref_create */
+    demod.rate_out = c->rate_in;
+    demod.rate_out2 = c->rate_out2;
+    demod.lpr.mode = c->mode;
+    demod.lpr.size = c->size;
+    demod.offset_tuning = c->offset_tuning;
+    demod.deemph = c->deemph;
+    demod.volume = c->volume;
+    demod.output_target = &output;
+    output.rate = c->rate_out2 ? c->rate_out2 : c->rate_in;
+    if (demod.deemph)                                /* :1575-1578 */
+        demod.deemph_lambda = (float) exp(-1.0 / ((double) output.rate * demod.deemph));
+
+    init_u8_f32_table();                             /* :1601-1603 */
+    init_lp_f32();
+    init_lp_real_f32(&demod);
+
+    output.filename = (char *) wav_path;             /* :1647-1656 */
+    output.file = InitWaveOut(output.filename, demod.lpr.mode);
+    if (!output.file) { free(_circbuffer); return -2; }
+    _audio_muted = 1;                                /* no audio device: the SDL_QueueAudio branch is skipped */
+    _isStartStream = true;                           /* :1665 */
+
+    pthread_create(&output.thread, NULL, output_thread_fn, (void *) (&output));   /* :1614-1618 */
+    pthread_create(&demod.thread, NULL, demod_thread_fn, (void *) (&demod));
+    pthread_create(&dongle.thread, NULL, dongle_thread_fn, (void *) (&dongle));
+
+    pthread_join(dongle.thread, NULL);               /* the file is exhausted */
+    /* let the rings drain: whole blocks in, whole clusters out (what is left never leaves the rings, as
+     * in the player) */
+    for (spins = 0; spins < 20000 && (_input_buffer_size >= MAXIMUM_BUF_LENGTH || _output_buffer_size >= CIRCBUFFCLUSTER); spins++)
+        usleep(1000);
+    usleep(20000);                                   /* a block or cluster that was in flight */
+    for (spins = 0; spins < 20000 && (_input_buffer_size >= MAXIMUM_BUF_LENGTH || _output_buffer_size >= CIRCBUFFCLUSTER); spins++)
+        usleep(1000);
+    _do_exit = 1;                                    /* the X key, :1846 */
+    pthread_join(demod.thread, NULL);
+    pthread_join(output.thread, NULL);
+
+    output.filename = 0;                             /* :1856-1859 */
+    CloseWaveOut(output.file);
+    demod_cleanup(&demod);
+    output_cleanup(&output);
+    controller_cleanup(&controller);
+    free(_circbuffer);
+    _circbuffer = NULL;
+    return 0;
+}
+
 #ifdef REF_CLI
 static double now_s(void)
 {

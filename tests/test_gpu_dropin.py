@@ -211,3 +211,28 @@ def test_fmb_player_wav_files_equal_the_reference_pipeline(tmp_path, flag, cfgna
     assert r.returncode == 0, r.stderr
     subprocess.run([REF_CLI, flag, files[0], str(tmp_path / "r.pcm")], check=True, capture_output=True)
     assert open(files[0] + ".pcm", "rb").read() == (tmp_path / "r.pcm").read_bytes()
+
+
+@pytest.mark.parametrize("cfgname,kind,blocks", [("stereo192", "fm_stereo", 9), ("stereo240", "random", 13),
+                                                 ("mono192", "fm_mono", 9), ("stereo192_off", "fm_stereo", 9)])
+def test_unmodified_player_threads_with_libfmb_interposed_write_the_same_wav(tmp_path, cfgname, kind, blocks):
+    """The strongest form of the drop-in claim: the reference's OWN dongle/demod/output threads (compiled
+    unmodified into oracle/_ref/libfmref.so) run a capture file twice in separate processes -- once bound to
+    the reference's CPU functions, once with rtl_fm_player_b200/libfmb.so first in the global symbol scope
+    (what LD_PRELOAD does for the real binary), so that their calls to init_*/rotate_90_u8_f32/u8_f32/
+    full_demod land in the CUDA drop-in.  The two WAV files must be byte-identical."""
+    import sys
+    c = CONFIGS[cfgname]
+    iq = make_input(cfgname, kind, 5, blocks)
+    cap = tmp_path / "cap.u8"
+    iq.tofile(cap)
+    outs = {}
+    for how in ("ref", "dropin"):
+        wav = tmp_path / f"{how}.wav"
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_player.py"), how, str(cap), str(wav),
+               str(c["rate_in"]), str(c["rate_out2"]), str(c["mode"]), str(c["size"]), str(c.get("offset_tuning", 0))]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and f"{blocks} chunks delivered" in r.stdout, r.stdout + r.stderr
+        outs[how] = wav.read_bytes()
+    assert len(outs["ref"]) > 260 + 32768
+    assert outs["dropin"] == outs["ref"]

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import rtl_fm_player_b200 as R
+from vectors import CONFIGS, make_input
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -325,3 +326,38 @@ def test_timeshift_ring_plays_what_the_reference_would(slots, n_streams):
         assert L.fm_timeshift_state(ts, C.byref(b), C.byref(w), C.byref(n)) == 0
         assert (b.value, w.value, n.value) == (refs[0].bottom, refs[0].full, slots)
     L.fm_timeshift_destroy(ts)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's own threads, offline (oracle/run_ref_player.py): harness consistency on the CPU
+# ------------------------------------------------------------------------------------------
+def run_ref_player(how, cap, wav, cfgname):
+    import subprocess
+    import sys
+    c = CONFIGS[cfgname]
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_player.py"), how, str(cap), str(wav),
+           str(c["rate_in"]), str(c["rate_out2"]), str(c["mode"]), str(c["size"]), str(c.get("offset_tuning", 0))]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("mono192", "fm_mono")])
+def test_threaded_reference_pipeline_writes_the_wav_of_its_block_loop(tmp_path, cfgname, kind):
+    """dongle_thread_fn + demod_thread_fn + output_thread_fn of the reference, fed by the product's file
+    source through the rtlsdr_read_async contract (back-pressured on the input ring), produce exactly the
+    WAV that the block loop (ref_run) + the reference's InitWaveOut/CloseWaveOut produce: nothing is lost or
+    reordered in the rings, and the short tail of the capture is dropped."""
+    from oracle.oracle_py import RefOracle
+    blocks = 9
+    iq = make_input(cfgname, kind, 3, blocks)
+    cap = tmp_path / "cap.u8"
+    np.concatenate([iq, np.zeros(1000, np.uint8)]).tofile(cap)          # + a short tail
+    out = run_ref_player("ref", cap, tmp_path / "threads.wav", cfgname)
+    assert f"{blocks} chunks delivered" in out
+    pcm = RefOracle(**CONFIGS[cfgname]).run(iq)
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfmref.so"))
+    ref.ref_wav_write.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t]
+    raw = np.ascontiguousarray(pcm).view(np.uint8)
+    assert ref.ref_wav_write(str(tmp_path / "loop.wav").encode(), CONFIGS[cfgname]["mode"], raw.ctypes.data, raw.size) == 0
+    assert (tmp_path / "threads.wav").read_bytes() == (tmp_path / "loop.wav").read_bytes()
