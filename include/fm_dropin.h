@@ -29,6 +29,13 @@
  *     fm_dropin_set_strict(1) it is written back after every full_demod.
  *   - d->lowpassed is not filled (nothing in the reference reads it after full_demod; RMSShadowBuf is
  *     write-only)
+ *   - supported decoder shapes: lpr.mode 0, or lpr.mode 1/2 with lpr.size 90 or 128 (the only values the
+ *     reference's CLI can set: demod_init :1184, -X :1474, -Y :1487); kernels are compiled for exactly these, any
+ *     other lpr.size in the struct is reported through the error hook (FMB_ERR_UNSUPPORTED), as is a stereo
+ *     rate_out/rate_out2 ratio between 2 and 3 whose in-place output (:593-597) would overwrite unread input
+ *     beyond the emulated first-sample case -- both at the FIRST full_demod, never in the middle of playback
+ *   - rate_out is honoured separately from rate_in (they differ under -o N, main :1510): the filters follow
+ *     rate_in (:419-429), the resampler ticks rate_out/rate_out2 (:485)
  *   - the functions are `void` like the reference's; a CUDA failure or an unsupported configuration calls
  *     the error hook (default: message on stderr, then abort()).  There is no CPU fallback.
  */

@@ -71,6 +71,9 @@ typedef struct fmb_config {
                                   SURVEY.md A.7).  0: ideal decoder                                 */
     float deemph_lambda;/* 0 (default): pole = (float)exp(-1/(rate_out2*deemph)) as main() computes it
                            (:1577).  > 0: use this value (the drop-in passes demod_state.deemph_lambda) */
+    int rate_out;      /* demod.rate_out: the "fast" rate of lp_real_f32's resampler (:485).  0 (default) =
+                          rate_in, as for every CLI setting but -o N (main: rate_in *= post_downsample, :1510,
+                          so the filters are designed for rate_in while the ticks run at rate_out/rate_out2) */
 } fmb_config;
 
 typedef struct fmb_handle fmb_handle;
@@ -118,10 +121,22 @@ int fmb_process(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t 
  * `stream` (a cudaStream_t) and returns at once.  The de-emphasis pass runs on
  * an internal stream so that it overlaps the next call's demodulation;
  * fmb_join() makes `stream` wait for everything enqueued so far.
+ *
+ * Threading: a handle is driven by ONE host thread at a time (like the reference's
+ * demod_state, which only demod_thread_fn touches, :855-933); calls on one handle are
+ * not re-entrant.  The caller MAY change `stream` between calls: the step then first
+ * waits (on the device, via an event) for the previous step's demodulation on the old
+ * stream, because that step wrote the carried state this one reads.  After a CUDA
+ * failure in the middle of a step the handle refuses further steps with FMB_ERR_STATE
+ * until fmb_reset().
  */
 int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, int16_t *pcm_dev, size_t pcm_pitch,
                        void *stream);
 int fmb_join(fmb_handle *h, void *stream);
+/* The handle's own compute stream (a cudaStream_t on cfg.device), for callers without one. */
+void *fmb_internal_stream(fmb_handle *h);
+/* Blocks until the handle's device has finished everything enqueued so far. */
+int fmb_sync(fmb_handle *h);
 
 /*
  * Pipelined host path (end-to-end number): submit enqueues H2D copy, kernels
@@ -206,21 +221,6 @@ const char *fmb_last_error(void);
 /* Number of CUDA kernels this library has launched in this process. */
 long fmb_launch_count(void);
 const char *fmb_version(void);
-
-/* ---- synthetic captures (fm_synth.c; host only) ------------------------------ */
-#define FMB_SYNTH_FM_STEREO 0   /* two tones, 19 kHz pilot, 38 kHz DSB-SC L-R, +-75 kHz, noise */
-#define FMB_SYNTH_FM_MONO 1     /* one tone, no pilot */
-#define FMB_SYNTH_RANDOM 2      /* uniform random bytes: hits every atan2 branch */
-#define FMB_SYNTH_CONST_0 3
-#define FMB_SYNTH_CONST_127 4
-#define FMB_SYNTH_CONST_128 5
-#define FMB_SYNTH_CONST_255 6
-#define FMB_SYNTH_ALT_0_255 7   /* I=0,Q=255: zero guards of the discriminator */
-#define FMB_SYNTH_IMPULSE 8     /* one 255 in constant 127 */
-#define FMB_SYNTH_CARRIER_OFF 9 /* carrier 90 kHz off centre: drives PCM into the clamp */
-/* Writes 2*n_samples bytes of IQ for samples [first_sample, first_sample+n_samples) of `stream`. */
-int fmb_synth_capture(int kind, int stream, int rate_in, int offset_tuning, uint64_t first_sample,
-                      uint64_t n_samples, uint8_t *iq);
 
 #ifdef __cplusplus
 }

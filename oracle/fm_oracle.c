@@ -7,7 +7,7 @@
  * Parity status: PINNED.  The reference has no golden vectors or tests
  * (SURVEY.md s4), so this port is pinned against the reference's own code
  * compiled unmodified (oracle/ref_harness.c -> oracle/_ref/libfmref.so):
- * tests/test_oracle_pinning.py requires bit-identical stage outputs and PCM on
+ * tests/test_oracle.py requires bit-identical stage outputs and PCM on
  * every vector family of SURVEY.md s8(d), and tests/golden/ holds PCM produced
  * by that reference build so the pin also holds where /root/reference is absent.
  *
@@ -43,6 +43,8 @@ struct fmo_cfg {
     double deemph;
     float volume;
     int inplace_quirk; /* 1: emulate the in-place overwrite of :593-597 (what the reference does) */
+    int rate_out;      /* demod.rate_out, the resampler's fast rate (:485); 0 = rate_in (they differ only under
+                          -o N: main does rate_in *= post_downsample, :1510) */
 };
 
 /* Same field order as fmb_stream_state (include/fmb.h) so tests can compare raw bytes. */
@@ -105,7 +107,7 @@ static void design(struct fmo *o)
         }
     }
     {
-        int out_rate = c->rate_out2 ? c->rate_out2 : c->rate_in; /* :1416-1419, :1512-1514 */
+        int out_rate = c->rate_out2 ? c->rate_out2 : (c->rate_out > 0 ? c->rate_out : c->rate_in); /* :1416-1419, :1512-1514 */
         o->lambda = c->deemph ? (float) exp(-1.0 / ((double) out_rate * c->deemph)) : 0.0f; /* :1577 */
     }
     o->pcm_scale = c->volume * 32768.0f; /* :717 */
@@ -268,7 +270,7 @@ int fmo_block(void *h, const uint8_t *iq, uint32_t len, int16_t *pcm, float *dem
      * the quirk is emulated, outputs are written back into it. */
     memcpy(work, o->dem, (size_t) n_dem * 4);
     if (c->rate_out2 > 0) {
-        const int fast = c->rate_in, slow = c->rate_out2; /* rate_out == rate_in, :485 */
+        const int fast = c->rate_out > 0 ? c->rate_out : c->rate_in, slow = c->rate_out2; /* fast = fm->rate_out, :485 */
         float *outbuf = c->inplace_quirk ? work : o->dem; /* o->dem is free to be overwritten now */
         memcpy(hb - FMO_HIST, st->br, sizeof st->br);
         memcpy(hm - FMO_HIST, st->bm, sizeof st->bm);

@@ -31,12 +31,13 @@ def build(which: str = "all") -> None:
 
 class _PortCfg(C.Structure):
     _fields_ = [("rate_in", C.c_int), ("rate_out2", C.c_int), ("mode", C.c_int), ("size", C.c_int),
-                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float), ("inplace_quirk", C.c_int)]
+                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float), ("inplace_quirk", C.c_int),
+                ("rate_out", C.c_int)]
 
 
 class _RefCfg(C.Structure):
     _fields_ = [("rate_in", C.c_int), ("rate_out2", C.c_int), ("mode", C.c_int), ("size", C.c_int),
-                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float)]
+                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float), ("rate_out", C.c_int)]
 
 
 class PortState(C.Structure):
@@ -53,7 +54,7 @@ class PortOracle:
     """One channel of the C restatement."""
 
     def __init__(self, rate_in=240000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.000050,
-                 volume=0.4, inplace_quirk=1):
+                 volume=0.4, inplace_quirk=1, rate_out=0):
         if not os.path.exists(PORT_PATH):
             build("port")
         self.lib = C.CDLL(PORT_PATH)
@@ -68,7 +69,7 @@ class PortOracle:
         self.lib.fmo_bench.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
         self.lib.fmo_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         self.lib.fmo_get_state.argtypes = [C.c_void_p, C.POINTER(PortState), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
-        self.cfg = _PortCfg(rate_in, rate_out2, mode, size, offset_tuning, deemph, volume, inplace_quirk)
+        self.cfg = _PortCfg(rate_in, rate_out2, mode, size, offset_tuning, deemph, volume, inplace_quirk, rate_out)
         self.h = self.lib.fmo_create(C.byref(self.cfg))
         if not self.h:
             raise ValueError("fmo_create rejected the configuration")
@@ -123,7 +124,8 @@ def ref_available() -> bool:
 class RefOracle:
     """One channel of the reference's own code (oracle/_ref/libfmref.so)."""
 
-    def __init__(self, rate_in=240000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.000050, volume=0.4):
+    def __init__(self, rate_in=240000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.000050, volume=0.4,
+                 rate_out=0):
         if not ref_available():
             raise FileNotFoundError(REF_PATH)
         self.lib = C.CDLL(REF_PATH)
@@ -139,7 +141,7 @@ class RefOracle:
         self.lib.ref_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         self.lib.ref_layout.restype = C.c_long
         self.lib.ref_layout.argtypes = [C.c_int]
-        self.cfg = _RefCfg(rate_in, rate_out2, mode, size, offset_tuning, deemph, volume)
+        self.cfg = _RefCfg(rate_in, rate_out2, mode, size, offset_tuning, deemph, volume, rate_out)
         self.h = self.lib.ref_create(C.byref(self.cfg))
 
     def __del__(self):

@@ -32,6 +32,8 @@ struct ref_cfg {
     int offset_tuning;  /* -E offset                               :1454-1457 */
     double deemph;      /* seconds, 0 = off                        :1169 */
     float volume;       /* :1181 */
+    int rate_out;       /* 0: = rate_in.  Else demod.rate_out as main leaves it under -o N: rate_in is the
+                           oversampled rate (rate_in *= post_downsample, :1510), rate_out stays at -s */
 };
 
 struct ref_inst {
@@ -51,6 +53,7 @@ void ref_default_cfg(struct ref_cfg *c)
     c->offset_tuning = 0;
     c->deemph = DEEMPHASIS_FM_EU;
     c->volume = 0.4f;
+    c->rate_out = 0;
 }
 
 void *ref_create(const struct ref_cfg *c)
@@ -59,14 +62,14 @@ void *ref_create(const struct ref_cfg *c)
     if (!r) return NULL;
     demod_init(&r->d);                       /* :1156 */
     r->d.rate_in = c->rate_in;
-    r->d.rate_out = c->rate_in;
+    r->d.rate_out = c->rate_out > 0 ? c->rate_out : c->rate_in;
     r->d.rate_out2 = c->rate_out2;
     r->d.lpr.mode = c->mode;
     r->d.lpr.size = c->size;
     r->d.offset_tuning = c->offset_tuning;
     r->d.deemph = c->deemph;
     r->d.volume = c->volume;
-    r->output_rate = c->rate_out2 ? c->rate_out2 : c->rate_in;   /* :1416, :1512-1514 */
+    r->output_rate = c->rate_out2 ? c->rate_out2 : (int) r->d.rate_out;   /* :1416, :1512-1514 */
     if (r->d.deemph)                         /* :1575-1578 */
         r->d.deemph_lambda = (float) exp(-1.0 / ((double) r->output_rate * r->d.deemph));
     if (!g_tables_ready) {                   /* :1601-1602 */
@@ -77,6 +80,10 @@ void *ref_create(const struct ref_cfg *c)
     init_lp_real_f32(&r->d);                 /* :1603 */
     return r;
 }
+
+/* the reference's own (de)init of the decoder rings on a live instance (:413-470), for the re-init test */
+void ref_deinit_lp_real(void *h) { deinit_lp_real_f32(&((struct ref_inst *) h)->d); }
+void ref_init_lp_real(void *h) { init_lp_real_f32(&((struct ref_inst *) h)->d); }
 
 void ref_destroy(void *h)
 {
@@ -287,7 +294,7 @@ int ref_player_run(const struct ref_cfg *c, const char *wav_path, ref_read_async
     output_init(&output);
     controller_init(&controller);
     demod.rate_in = c->rate_in;                      /* the flags that change numerics, as ref_create */
-    demod.rate_out = c->rate_in;
+    demod.rate_out = c->rate_out > 0 ? c->rate_out : c->rate_in;
     demod.rate_out2 = c->rate_out2;
     demod.lpr.mode = c->mode;
     demod.lpr.size = c->size;
@@ -295,7 +302,7 @@ int ref_player_run(const struct ref_cfg *c, const char *wav_path, ref_read_async
     demod.deemph = c->deemph;
     demod.volume = c->volume;
     demod.output_target = &output;
-    output.rate = c->rate_out2 ? c->rate_out2 : c->rate_in;
+    output.rate = c->rate_out2 ? c->rate_out2 : (int) demod.rate_out;
     if (demod.deemph)                                /* :1575-1578 */
         demod.deemph_lambda = (float) exp(-1.0 / ((double) output.rate * demod.deemph));
 
@@ -362,6 +369,10 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "-E") && i + 1 < argc) { if (!strcmp(argv[++i], "offset")) c.offset_tuning = 1; }
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) c.rate_in = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-r") && i + 1 < argc) c.rate_out2 = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) { /* main: rate_in *= post_downsample (:1422, :1510) */
+            const int n = atoi(argv[++i]);
+            if (n > 1) { c.rate_out = c.rate_in; c.rate_in *= n; }
+        }
         else if (!strcmp(argv[i], "-m") && i + 1 < argc) c.mode = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-z") && i + 1 < argc) c.size = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) repeat = atoi(argv[++i]);

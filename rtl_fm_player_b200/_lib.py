@@ -21,12 +21,6 @@ FMB_PRECISION_EXACT, FMB_PRECISION_FMA = 0, 1
 FMB_PIPE_DEPTH = 3
 FMB_HIST = 128
 
-SYNTH_KINDS = {
-    "fm_stereo": 0, "fm_mono": 1, "random": 2, "const0": 3, "const127": 4, "const128": 5,
-    "const255": 6, "alt_0_255": 7, "impulse": 8, "carrier_off": 9,
-}
-
-
 class FmbConfig(C.Structure):
     """struct fmb_config (include/fmb.h) == the demod_state fields that fix numerics."""
     _fields_ = [
@@ -34,7 +28,7 @@ class FmbConfig(C.Structure):
         ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float),
         ("n_streams", C.c_int), ("block_bytes", C.c_int), ("device", C.c_int),
         ("precision", C.c_int), ("segments", C.c_int), ("emulate_inplace_quirk", C.c_int),
-        ("deemph_lambda", C.c_float),
+        ("deemph_lambda", C.c_float), ("rate_out", C.c_int),
     ]
 
 
@@ -89,7 +83,24 @@ SIGNATURES = {
     "fmb_last_error": (C.c_char_p, []),
     "fmb_launch_count": (C.c_long, []),
     "fmb_version": (C.c_char_p, []),
-    "fmb_synth_capture": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "fmb_internal_stream": (C.c_void_p, [C.c_void_p]),
+    "fmb_sync": (C.c_int, [C.c_void_p]),
+    # include/fmb_multi.h: the C multi-GPU host (one worker thread per device)
+    "fmb_multi_create": (C.c_int, [C.POINTER(FmbConfig), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "fmb_multi_destroy": (C.c_int, [C.c_void_p]),
+    "fmb_multi_shards": (C.c_int, [C.c_void_p]),
+    "fmb_multi_shard_range": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fmb_multi_handle": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "fmb_multi_next_out_count": (C.c_int, [C.c_void_p]),
+    "fmb_multi_max_out_count": (C.c_int, [C.c_void_p]),
+    "fmb_multi_reset": (C.c_int, [C.c_void_p]),
+    "fmb_multi_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "fmb_multi_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "fmb_multi_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "fmb_multi_process_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t]),
+    "fmb_multi_sync": (C.c_int, [C.c_void_p]),
+    "fmb_parse_device_list": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int]),
+    "fmb_device_count": (C.c_int, []),
 }
 
 

@@ -34,6 +34,7 @@ class DemodConfig:
     segments: int = 0
     emulate_inplace_quirk: int = 1
     deemph_lambda: float = 0.0
+    rate_out: int = 0          # demod.rate_out (the resampler's fast rate, :485); 0 = rate_in
 
     @classmethod
     def stereo_192k(cls, **kw) -> "DemodConfig":

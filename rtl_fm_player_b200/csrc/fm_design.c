@@ -70,7 +70,8 @@ int fmb_design_tables(const fmb_config *cfg, fmb_tables *t)
 
     /* de-emphasis pole at the OUTPUT rate (:1577; output.rate follows -r, :1416-1419) */
     {
-        const int out_rate = cfg->rate_out2 > 0 ? cfg->rate_out2 : cfg->rate_in;
+        const int fast = cfg->rate_out > 0 ? cfg->rate_out : cfg->rate_in;          /* output.rate = demod.rate_out, :1512-1514 */
+        const int out_rate = cfg->rate_out2 > 0 ? cfg->rate_out2 : fast;
         t->lambda = cfg->deemph != 0.0 ? (float) exp(-1.0 / ((double) out_rate * cfg->deemph)) : 0.0f;
         if (cfg->deemph != 0.0 && cfg->deemph_lambda > 0.0f) t->lambda = cfg->deemph_lambda;
     }

@@ -131,7 +131,9 @@ static void config_from_struct(struct shim *s, fmb_config *c, uint32_t buf_len)
 {
     struct demod_state *d = s->d;
     fmb_default_config(c);
-    c->rate_in = F(d, int, FMD_OFF_rate_in);
+    c->rate_in = F(d, int, FMD_OFF_rate_in);         /* the filters' rate (init_lp_real_f32, :419-429) */
+    c->rate_out = F(d, int, FMD_OFF_rate_out);       /* the resampler's fast rate (lp_real_f32, :485); differs from
+                                                        rate_in under -o N (main: rate_in *= post_downsample, :1510) */
     c->rate_out2 = F(d, int, FMD_OFF_rate_out2);
     c->mode = LPR(d, int, FMD_LPR_OFF_mode);
     c->size = LPR(d, int, FMD_LPR_OFF_size);
@@ -148,7 +150,7 @@ static void config_from_struct(struct shim *s, fmb_config *c, uint32_t buf_len)
 
 static int same_config(const fmb_config *a, const fmb_config *b)
 {
-    return a->rate_in == b->rate_in && a->rate_out2 == b->rate_out2 && a->mode == b->mode && a->size == b->size &&
+    return a->rate_in == b->rate_in && a->rate_out == b->rate_out && a->rate_out2 == b->rate_out2 && a->mode == b->mode && a->size == b->size &&
            a->offset_tuning == b->offset_tuning && a->deemph == b->deemph && a->deemph_lambda == b->deemph_lambda &&
            a->block_bytes == b->block_bytes && a->device == b->device;
 }
@@ -192,6 +194,18 @@ void init_lp_real_f32(struct demod_state *d)
     fmb_tables t;
     int rc;
     const int size = LPR(d, int, FMD_LPR_OFF_size), taps = size >> 1;
+    {
+        /* Called again on a struct that already has a GPU context: the reference's callocs below start the
+         * decoder rings from zero (:430-436) and leave everything else (lowpass_tb, pre_r/j, de-emphasis, resampler
+         * phase) alone.  So: bring the struct up to date, then forget the GPU copy -- the context is rebuilt
+         * from the struct, fresh rings included, at the next full_demod. */
+        struct shim *old = find(d, 0);
+        if (old) {
+            if (old->h && (rc = export_state(old)) != FMB_OK) fail("init_lp_real_f32: exporting the GPU state", rc);
+            drop_handle(old);
+            old->pos = 0;
+        }
+    }
     fmb_default_config(&c);
     c.rate_in = F(d, int, FMD_OFF_rate_in);
     c.size = size;
@@ -262,7 +276,9 @@ void full_demod(struct demod_state *d)
         fail("full_demod without a preceding rotate_90_u8_f32()/u8_f32() on this block", FMB_ERR_STATE);
         return;
     }
-    if (F(d, int, FMD_OFF_post_downsample) > 1) { /* empty block in the reference (:776-779): nothing to mirror */ }
+    /* d->post_downsample > 1 is an empty block in full_demod itself (:776-779, "for float not implemented"): its
+     * only effect on this path is main()'s rate_in *= post_downsample (:1510), which config_from_struct honours by
+     * taking the filters' rate from rate_in and the resampler's from rate_out. */
     config_from_struct(s, &c, buf_len);
     if (!s->h || !same_config(&c, &s->cfg)) {
         if (s->h) { export_state(s); drop_handle(s); }
@@ -273,7 +289,14 @@ void full_demod(struct demod_state *d)
         rc = fmb_host_alloc((void **) &s->pin_iq, (size_t) c.block_bytes);
         if (rc == FMB_OK) rc = fmb_host_alloc((void **) &s->pin_pcm, (s->pcm_cap + 8) * sizeof(int16_t));
         if (rc == FMB_OK) rc = import_state(s);
-        if (rc != FMB_OK) { fail("setting up the GPU context", rc); return; }
+        if (rc != FMB_OK) {
+            /* with an error hook installed fail() returns: leave no half-built context behind, so that the
+             * next call starts over (and reports again) instead of copying into a NULL staging buffer or
+             * continuing silently from zero state */
+            fail("setting up the GPU context", rc);
+            drop_handle(s);
+            return;
+        }
     } else if (c.volume != s->cfg.volume) {
         rc = fmb_set_volume(s->h, c.volume);
         if (rc != FMB_OK) { fail("fmb_set_volume", rc); return; }

@@ -4,8 +4,12 @@
  * branch of output_thread_fn :955-1005), in plain C on top of the C ABI:
  *
  *   one capture file per FM channel  --filesrc_read_async (one thread per channel, 262144-byte chunks)-->
- *   pinned batch buffer [channel][block]  --fmb_submit / fmb_wait (H2D, CUDA kernels, D2H)-->
+ *   pinned batch buffer [channel][block]  --fmb_multi_submit / fmb_multi_wait (per device: H2D, CUDA kernels, D2H)-->
  *   per-channel PCM  --fm_wav (reference WAV header + 32768-byte clusters) or raw .pcm-->
+ *
+ * The channels are sharded by index over the devices given with -d (default: device 0), one worker thread per
+ * device (include/fmb_multi.h); every device reads its slice of the one pinned input buffer and writes its
+ * slice of the one pinned PCM buffer, so the host gathers nothing.
  *
  * Flags follow the reference's where they exist (-X -Y -s -r -E offset, :1389-1508).
  */
@@ -19,6 +23,7 @@
 #include "fm_filesrc.h"
 #include "fm_wav.h"
 #include "fmb.h"
+#include "fmb_multi.h"
 
 #define NBUF FMB_PIPE_DEPTH
 
@@ -89,9 +94,10 @@ static void usage(void)
     fprintf(stderr,
             "fmb_player -- batched offline FM demodulator (B200), one rtl_sdr-format uint8 IQ capture per channel\n"
             "usage: fmb_player [-X | -Y] [-s rate_in] [-r rate_out2] [-E offset] [-m lpr_mode] [-z lpr_size]\n"
-            "                  [-v volume] [-w] [-o out_dir] [-d cuda_device] [-P exact|fma] [-R speed] capture.u8 ...\n"
+            "                  [-v volume] [-w] [-o out_dir] [-d cuda_devices] [-P exact|fma] [-R speed] capture.u8 ...\n"
             "  -X  stereo preset 192k/48k, 90 taps   -Y  mono preset 192k/48k, 128 taps   (as rtl_fm_player)\n"
             "  -w  write <name>.wav with the reference's header and 32768-byte cluster rule (default: raw <name>.pcm)\n"
+            "  -d  CUDA devices to shard the channels over, e.g. 0-7 or 0,2,4 (default 0); at least one channel per device\n"
             "  -R  pace the captures at `speed` x real time (default: as fast as the GPU takes them)\n");
 }
 
@@ -110,8 +116,11 @@ int main(int argc, char **argv)
     long k, submitted = 0, total_blocks = 0;
     int tickets[NBUF];
     int *n_outs;
+    int devices[64], n_devices = 1;
+    fmb_multi *h = NULL;
 
     memset(&P, 0, sizeof P);
+    devices[0] = 0;
     fmb_default_config(&P.cfg);
     for (i = 1; i < argc; ++i) {
         const char *a = argv[i];
@@ -123,7 +132,10 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-m") && i + 1 < argc) P.cfg.mode = atoi(argv[++i]);
         else if (!strcmp(a, "-z") && i + 1 < argc) P.cfg.size = atoi(argv[++i]);
         else if (!strcmp(a, "-v") && i + 1 < argc) P.cfg.volume = (float) atof(argv[++i]);
-        else if (!strcmp(a, "-d") && i + 1 < argc) P.cfg.device = atoi(argv[++i]);
+        else if (!strcmp(a, "-d") && i + 1 < argc) {
+            n_devices = fmb_parse_device_list(argv[++i], devices, 64);
+            if (n_devices < 1) { fprintf(stderr, "-d: %s\n", fmb_last_error()); return 2; }
+        }
         else if (!strcmp(a, "-o") && i + 1 < argc) out_dir = argv[++i];
         else if (!strcmp(a, "-R") && i + 1 < argc) speed = atof(argv[++i]);
         else if (!strcmp(a, "-P") && i + 1 < argc) P.cfg.precision = !strcmp(argv[++i], "fma") ? FMB_PRECISION_FMA : FMB_PRECISION_EXACT;
@@ -141,11 +153,11 @@ int main(int argc, char **argv)
     pthread_mutex_init(&P.mu, NULL);
     pthread_cond_init(&P.cv, NULL);
 
-    fmb_handle *h = NULL;
-    fmb_bind_thread_to_device_node(P.cfg.device); /* best effort: node-local pinned buffers */
-    rc = fmb_create(&P.cfg, &h);
-    if (rc != FMB_OK) { fprintf(stderr, "fmb_create: %s\n", fmb_last_error()); return 1; }
-    P.pcm_pitch = ((size_t) fmb_max_out_count(h) + 7) & ~(size_t) 7;
+    if (n_devices > P.n) n_devices = P.n;          /* fewer channels than devices: use the first P.n */
+    if (n_devices == 1) fmb_bind_thread_to_device_node(devices[0]); /* best effort: node-local pinned buffers */
+    rc = fmb_multi_create(&P.cfg, devices, n_devices, &h);
+    if (rc != FMB_OK) { fprintf(stderr, "fmb_multi_create: %s\n", fmb_last_error()); return 1; }
+    P.pcm_pitch = ((size_t) fmb_multi_max_out_count(h) + 7) & ~(size_t) 7;
     for (i = 0; i < NBUF; ++i) {
         if (fmb_host_alloc((void **) &P.iq[i], (size_t) P.n * (size_t) P.cfg.block_bytes) != FMB_OK ||
             fmb_host_alloc((void **) &P.pcm[i], (size_t) P.n * P.pcm_pitch * sizeof(int16_t)) != FMB_OK) {
@@ -187,16 +199,16 @@ int main(int argc, char **argv)
         if (live > 0) {
             for (i = 0; i < P.n; ++i) /* ended channels get mid-scale bytes; their PCM is not written */
                 if (P.ch[i].produced <= k) memset(P.iq[k % NBUF] + (size_t) i * (size_t) P.cfg.block_bytes, 127, (size_t) P.cfg.block_bytes);
-            rc = fmb_submit(h, P.iq[k % NBUF], (size_t) P.cfg.block_bytes, P.pcm[k % NBUF], P.pcm_pitch, &tickets[k % NBUF]);
-            if (rc != FMB_OK) { fprintf(stderr, "fmb_submit: %s\n", fmb_last_error()); return 1; }
+            rc = fmb_multi_submit(h, P.iq[k % NBUF], (size_t) P.cfg.block_bytes, P.pcm[k % NBUF], P.pcm_pitch, &tickets[k % NBUF]);
+            if (rc != FMB_OK) { fprintf(stderr, "fmb_multi_submit: %s\n", fmb_last_error()); return 1; }
             submitted = k + 1;
         }
         /* retire block k-(NBUF-1) (or everything left once the inputs have ended) */
         {
             long upto = live > 0 ? submitted - (NBUF - 1) : submitted, j;
             for (j = P.consumed; j < upto; ++j) {
-                rc = fmb_wait(h, tickets[j % NBUF], n_outs);   /* result_len of this block, per channel */
-                if (rc != FMB_OK) { fprintf(stderr, "fmb_wait: %s\n", fmb_last_error()); return 1; }
+                rc = fmb_multi_wait(h, tickets[j % NBUF], n_outs);   /* result_len of this block, per channel */
+                if (rc != FMB_OK) { fprintf(stderr, "fmb_multi_wait: %s\n", fmb_last_error()); return 1; }
                 n_out = n_outs[0];
                 for (i = 0; i < P.n; ++i) {
                     struct chan *c = &P.ch[i];
@@ -216,8 +228,8 @@ int main(int argc, char **argv)
     }
     {
         const double dt = now_s() - t0;
-        fprintf(stderr, "fmb_player: %d channel(s), %ld channel-blocks (%.1f M IQ samples) in %.3f s = %.1f Msamples/s\n",
-                P.n, total_blocks, (double) total_blocks * (P.cfg.block_bytes / 2) * 1e-6, dt,
+        fprintf(stderr, "fmb_player: %d channel(s) on %d device(s), %ld channel-blocks (%.1f M IQ samples) in %.3f s = %.1f Msamples/s\n",
+                P.n, n_devices, total_blocks, (double) total_blocks * (P.cfg.block_bytes / 2) * 1e-6, dt,
                 (double) total_blocks * (P.cfg.block_bytes / 2) * 1e-6 / (dt > 0 ? dt : 1));
     }
     for (i = 0; i < P.n; ++i) {
@@ -227,7 +239,7 @@ int main(int argc, char **argv)
         filesrc_close(P.ch[i].src);
     }
     for (i = 0; i < NBUF; ++i) { fmb_host_free(P.iq[i]); fmb_host_free(P.pcm[i]); }
-    fmb_destroy(h);
+    fmb_multi_destroy(h);
     free(P.ch);
     free(n_outs);
     return 0;

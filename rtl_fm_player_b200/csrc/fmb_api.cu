@@ -86,6 +86,12 @@ struct fmb_handle {
     float *d_dem = nullptr;          /* debug tap */
     int debug = 0;
     int last_n_out = 0, last_lr = 0;
+    int fast = 0;                    /* the resampler's fast rate: cfg.rate_out, or rate_in when that is 0 (:485) */
+    /* the caller stream of the previous step: when it changes, the new stream first waits for that step's demod
+     * kernel (it wrote the carried state and drew from the ticket counter this step continues from) */
+    cudaStream_t last_stream = nullptr;
+    bool have_last_stream = false;
+    bool poisoned = false;           /* a CUDA call failed in the middle of a step: bookkeeping and device state disagree */
     /* streams / events */
     cudaStream_t s_aux = nullptr, s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_demod[kLrBufs] = {}, ev_deemph[kLrBufs] = {};
@@ -110,7 +116,7 @@ int out_count_for(const fmb_handle *h, int phase)
 {
     const fmb_config &c = h->cfg;
     if (c.rate_out2 <= 0) return h->n_dem;
-    const long long ticks = ((long long) phase + (long long) h->n_dem * c.rate_out2) / c.rate_in;
+    const long long ticks = ((long long) phase + (long long) h->n_dem * c.rate_out2) / h->fast;
     return (int) (c.mode == 2 ? 2 * ticks : ticks);
 }
 
@@ -118,22 +124,21 @@ int next_phase(const fmb_handle *h, int phase)
 {
     const fmb_config &c = h->cfg;
     if (c.rate_out2 <= 0) return phase;
-    return (int) (((long long) phase + (long long) h->n_dem * c.rate_out2) % c.rate_in);
+    return (int) (((long long) phase + (long long) h->n_dem * c.rate_out2) % h->fast);
 }
 
 /* Does the reference's in-place output overwrite (src/rtl_fm_player.c:593-597)
  * hit an input that is still to be read, anywhere but the handled case
- * "tick on sample 0 clobbers sample 1"?  Simulates one block's index walk. */
-bool unhandled_inplace_hazard(const fmb_handle *h, int phase)
+ * "tick on sample 0 clobbers sample 1"?  Simulates one block's index walk (the definition). */
+bool inplace_hazard_by_walk(const fmb_handle *h, int phase)
 {
     const fmb_config &c = h->cfg;
-    if (c.mode != 2 || c.rate_out2 <= 0) return false;
     long long p = phase;
     int o = 0;
     for (int i = 0; i < h->n_dem; ++i) {
         p += c.rate_out2;
-        if (p >= c.rate_in) {
-            p -= c.rate_in;
+        if (p >= h->fast) {
+            p -= h->fast;
             /* writes ib[o], ib[o+1] after reading ib[i] */
             if (o + 1 > i && !(i == 0)) return true;
             o += 2;
@@ -142,10 +147,45 @@ bool unhandled_inplace_hazard(const fmb_handle *h, int phase)
     return false;
 }
 
+/* The same in O(1).  Tick k (0-based) of a block that starts at phase p fires on sample
+ * i_k = ceil(((k+1)*fast - p) / slow) - 1 and then overwrites ib[2k], ib[2k+1]; it clobbers unread input iff
+ * 2k+1 > i_k (k = 0 can only produce the handled case i_0 = 0).  With fast >= 2*slow consecutive ticks are at
+ * least 2 samples apart, so i_k - (2k+1) never decreases with k: there is a hazard iff tick 1 has one. */
+bool inplace_hazard(const fmb_handle *h, int phase)
+{
+    const fmb_config &c = h->cfg;
+    if (c.mode != 2 || c.rate_out2 <= 0) return false;
+    const long long slow = c.rate_out2, fast = h->fast;
+    const long long i1 = (2 * fast - phase + slow - 1) / slow - 1;
+    return i1 < h->n_dem && i1 < 3;
+}
+
+/* Every block-start phase the handle can reach from `phase0` (the schedule is periodic: at most fast/gcd
+ * steps) is checked once, at create / state-import time, so that an unsupported ratio is refused there and
+ * not in the middle of playback.  The first phases are also walked sample by sample against the O(1) rule. */
+int check_inplace_cycle(const fmb_handle *h, int phase0)
+{
+    const fmb_config &c = h->cfg;
+    if (c.mode != 2 || c.rate_out2 <= 0 || !c.emulate_inplace_quirk) return FMB_OK;
+    int phase = phase0;
+    for (long long step = 0; step <= (long long) h->fast; ++step) {
+        const bool hz = inplace_hazard(h, phase);
+        if (step < 48 && hz != inplace_hazard_by_walk(h, phase))
+            return set_err(FMB_ERR_STATE, "internal: in-place hazard rule disagrees with the sample walk");
+        if (hz)
+            return set_err(FMB_ERR_UNSUPPORTED,
+                           "rate_out/rate_out2 ratio makes the reference's in-place stereo output overwrite unread input "
+                           "beyond the emulated first-sample case (happens for ratios between 2 and 3)");
+        phase = next_phase(h, phase);
+        if (phase == phase0) break;
+    }
+    return FMB_OK;
+}
+
 bool tick_on_first_sample(const fmb_handle *h, int phase)
 {
     const fmb_config &c = h->cfg;
-    return c.mode == 2 && c.rate_out2 > 0 && (long long) phase + c.rate_out2 >= c.rate_in;
+    return c.mode == 2 && c.rate_out2 > 0 && (long long) phase + c.rate_out2 >= h->fast;
 }
 
 void destroy_events(cudaEvent_t *ev, int n)
@@ -189,17 +229,21 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
                  cudaStream_t sm, int *n_out_ret)
 {
     const fmb_config &c = h->cfg;
+    if (h->poisoned)
+        return set_err(FMB_ERR_STATE, "an earlier CUDA failure left this handle half-advanced; fmb_reset() or destroy it");
     const int n_out = out_count_for(h, h->phase);
     if ((size_t) n_out > pcm_pitch) return set_err(FMB_ERR_ARG, "pcm_pitch smaller than fmb_next_out_count()");
     if (iq_pitch < (size_t) c.block_bytes || (iq_pitch & 15) || ((uintptr_t) d_iq & 15))
         return set_err(FMB_ERR_ARG, "iq pointer/pitch must be 16-byte aligned and pitch >= block_bytes");
     const bool quirk = c.emulate_inplace_quirk && tick_on_first_sample(h, h->phase);
-    if (c.emulate_inplace_quirk && unhandled_inplace_hazard(h, h->phase))
-        return set_err(FMB_ERR_UNSUPPORTED,
-                       "rate_in/rate_out2 ratio makes the reference's in-place stereo output overwrite unread input "
-                       "beyond the emulated first-sample case");
+    if (c.emulate_inplace_quirk && inplace_hazard(h, h->phase))   /* refused at create/set_state; cheap re-check */
+        return set_err(FMB_ERR_UNSUPPORTED, "in-place stereo output would overwrite unread input (see fmb_create)");
 
     const int b = h->lr_cur;
+    /* Nothing below may fail between the first enqueue and the bookkeeping at the end without poisoning the
+     * handle; these waits come first and change nothing if they fail. */
+    /* a different caller stream than last time: order this step behind the previous step's demod kernel */
+    if (h->have_last_stream && h->last_stream != sm) CU(cudaStreamWaitEvent(sm, h->ev_demod[h->last_lr], 0));
     /* the de-emphasis pass that last read d_lr[b] must be done before we overwrite it */
     if (h->deemph_pending[b]) CU(cudaStreamWaitEvent(sm, h->ev_deemph[b], 0));
 
@@ -217,22 +261,23 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     kp.grid = h->grid;
     kp.n_dem = h->n_dem;
     if (c.rate_out2 > 0) {
-        kp.slow = c.rate_out2; kp.fast = c.rate_in; kp.phase0 = h->phase;
-        if (c.rate_in % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0) {
-            kp.dec = c.rate_in / c.rate_out2;
+        kp.slow = c.rate_out2; kp.fast = h->fast; kp.phase0 = h->phase;
+        if (h->fast % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0) {
+            kp.dec = h->fast / c.rate_out2;
             kp.dec_c0 = h->phase / c.rate_out2;
         }
     } else { /* lp_real_f32 skipped: every sample is an output */
         kp.slow = 1; kp.fast = 1; kp.phase0 = 0; kp.dec = 1; kp.dec_c0 = 0;
     }
     kp.quirk = quirk ? 1 : 0;
+    unsigned int ticket_step = 0;      /* tickets this launch consumes; committed with the rest of the bookkeeping */
     if (h->chunk > 0) {
         const int spb = h->n_dem / FMB_NSUB;
         kp.chunk = h->chunk;
         kp.n_whole = h->n_whole;
         kp.tickets = h->d_tickets;
         kp.ticket_base = h->ticket_base;
-        h->ticket_base += (unsigned int) (h->n_whole + (c.n_streams - h->n_whole) * (spb / h->chunk) + h->grid);
+        ticket_step = (unsigned int) (h->n_whole + (c.n_streams - h->n_whole) * (spb / h->chunk) + h->grid);
     }
 
     fmb_config kc = c;
@@ -241,13 +286,19 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     const bool prof = h->profile && h->pcount[0] < kProfMax && h->pcount[1] < kProfMax;
     if (prof) CU(cudaEventRecord(h->pev[0][0][h->pcount[0]], sm));
     cudaError_t e = (cudaError_t) fmb_launch_demod(&kc, &kp, &h->tab, sm);
-    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_demod_kernel launch", e);
+    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_demod_kernel launch", e);   /* nothing enqueued, nothing advanced */
     g_launches++;
-    if (prof) { CU(cudaEventRecord(h->pev[0][1][h->pcount[0]], sm)); h->pcount[0]++; }
-    CU(cudaEventRecord(h->ev_demod[b], sm));
+    /* from here on the device state is ahead of the bookkeeping until the end of this function */
+#define CUP(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { h->poisoned = true; return set_err(FMB_ERR_CUDA, #call, e_); }     \
+    } while (0)
+    if (prof) { CUP(cudaEventRecord(h->pev[0][1][h->pcount[0]], sm)); h->pcount[0]++; }
+    CUP(cudaEventRecord(h->ev_demod[b], sm));
 
     /* de-emphasis + int16 on the aux stream, in step order */
-    CU(cudaStreamWaitEvent(h->s_aux, h->ev_demod[b], 0));
+    CUP(cudaStreamWaitEvent(h->s_aux, h->ev_demod[b], 0));
     fmb_dparams dp;
     memset(&dp, 0, sizeof dp);
     dp.lr = h->d_lr[b];
@@ -262,17 +313,21 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     dp.lambda = h->tab.lambda;
     dp.pcm_scale = h->tab.pcm_scale;
     dp.fallbacks = h->d_fallbacks;
-    if (prof) CU(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
+    if (prof) CUP(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
 #ifdef FMB_TUNE_SKIP_DEEMPH   /* tools/build_variant.sh only: timing experiment, PCM is not produced */
     e = cudaSuccess;
 #else
     e = (cudaError_t) fmb_launch_deemph(&dp, h->s_aux);
 #endif
-    if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "fmb_deemph_kernel launch", e);
+    if (e != cudaSuccess) { h->poisoned = true; return set_err(FMB_ERR_CUDA, "fmb_deemph_kernel launch", e); }
     g_launches++;
-    if (prof) { CU(cudaEventRecord(h->pev[1][1][h->pcount[1]], h->s_aux)); h->pcount[1]++; }
-    CU(cudaEventRecord(h->ev_deemph[b], h->s_aux));
+    if (prof) { CUP(cudaEventRecord(h->pev[1][1][h->pcount[1]], h->s_aux)); h->pcount[1]++; }
+    CUP(cudaEventRecord(h->ev_deemph[b], h->s_aux));
+#undef CUP
     h->deemph_pending[b] = true;
+    h->ticket_base += ticket_step;
+    h->last_stream = sm;
+    h->have_last_stream = true;
 
     h->last_n_out = n_out;
     h->last_lr = b;
@@ -289,6 +344,13 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
 extern "C" {
 
 const char *fmb_last_error(void) { return g_err; }
+void fmb_set_last_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
+int fmb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 long fmb_launch_count(void) { return g_launches.load(); }
 const char *fmb_version(void) { return "rtl_fm_player_b200 0.1 (sm_100a)"; }
 
@@ -310,6 +372,7 @@ int fmb_default_config(fmb_config *cfg)
     cfg->segments = 0;
     cfg->emulate_inplace_quirk = 1;
     cfg->deemph_lambda = 0.0f;
+    cfg->rate_out = 0;         /* = rate_in (:1159; they differ only under -o N, :1510) */
     return FMB_OK;
 }
 
@@ -337,12 +400,14 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
         return set_err(FMB_ERR_ARG, "block_bytes must be a positive multiple of 32768");
     if (cfg->precision != FMB_PRECISION_EXACT && cfg->precision != FMB_PRECISION_FMA)
         return set_err(FMB_ERR_ARG, "bad precision");
-    if (cfg->rate_out2 > cfg->rate_in) return set_err(FMB_ERR_UNSUPPORTED, "rate_out2 > rate_in");
-    /* the tick schedule of a sub-tile is evaluated in 32-bit arithmetic: (ticks + 1) * rate_in must fit */
-    if ((long long) (FMB_NSUB + FMB_NT + 2) * cfg->rate_in >= (1LL << 32))
-        return set_err(FMB_ERR_UNSUPPORTED, "rate_in too high (limit about 1.86 MHz after the /8 channel filter)");
-    if (cfg->mode == 2 && cfg->rate_out2 > 0 && 2LL * cfg->rate_out2 > cfg->rate_in)
-        return set_err(FMB_ERR_UNSUPPORTED, "stereo needs rate_in >= 2*rate_out2 (in-place output, reference :593-597)");
+    if (cfg->rate_out < 0) return set_err(FMB_ERR_ARG, "bad rate_out");
+    const int fast = cfg->rate_out > 0 ? cfg->rate_out : cfg->rate_in;
+    if (cfg->rate_out2 > fast) return set_err(FMB_ERR_UNSUPPORTED, "rate_out2 > rate_out");
+    /* the tick schedule of a sub-tile is evaluated in 32-bit arithmetic: (ticks + 1) * rate_out must fit */
+    if ((long long) (FMB_NSUB + FMB_NT + 2) * fast >= (1LL << 32))
+        return set_err(FMB_ERR_UNSUPPORTED, "rate_out too high (limit about 1.86 MHz after the /8 channel filter)");
+    if (cfg->mode == 2 && cfg->rate_out2 > 0 && 2LL * cfg->rate_out2 > fast)
+        return set_err(FMB_ERR_UNSUPPORTED, "stereo needs rate_out >= 2*rate_out2 (in-place output, reference :593-597)");
     {
         const int kmode = cfg->rate_out2 > 0 ? cfg->mode : 0;
         if (fmb_demod_supported(kmode, cfg->size) != 0)
@@ -362,6 +427,9 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     int rc = fmb_design_tables(cfg, &h->tab);
     if (rc != FMB_OK) { delete h; return set_err(rc, "filter design rejected the configuration"); }
     h->n_dem = cfg->block_bytes / 16;
+    h->fast = fast;
+    rc = check_inplace_cycle(h, 0);
+    if (rc != FMB_OK) { delete h; return rc; }
     {
         /* CTAs: the n_streams x (block/2048 samples) work units are dealt out evenly ("stream-K").
          * Default: one CTA per resident slot (SMs x occupancy); cfg.segments > 0 forces n_streams x segments. */
@@ -391,7 +459,7 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     h->blocks_done = 0;
     /* upper bound of outputs per step */
     if (cfg->rate_out2 > 0) {
-        const long long t = ((long long) cfg->rate_in - 1 + (long long) h->n_dem * cfg->rate_out2) / cfg->rate_in;
+        const long long t = ((long long) fast - 1 + (long long) h->n_dem * cfg->rate_out2) / fast;
         h->max_out = (int) (cfg->mode == 2 ? 2 * t : t);
     } else {
         h->max_out = h->n_dem;
@@ -514,8 +582,12 @@ int fmb_reset(fmb_handle *h)
     const size_t st_bytes = sizeof(fmb_stream_state) * (size_t) h->cfg.n_streams;
     for (int i = 0; i < 2; ++i) CU(cudaMemset(h->d_state[i], 0, st_bytes));
     CU(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) h->cfg.n_streams));
+    CU(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
+    h->ticket_base = 0;
     h->phase = 0;
     h->blocks_done = 0;
+    h->poisoned = false;
+    h->have_last_stream = false;
     for (bool &pend : h->deemph_pending) pend = false;
     for (auto &s : h->slot) s.busy = false;
     return FMB_OK;
@@ -537,6 +609,16 @@ int fmb_join(fmb_handle *h, void *stream)
     if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
     for (int b = 0; b < kLrBufs; ++b)
         if (h->deemph_pending[b]) CU(cudaStreamWaitEvent((cudaStream_t) stream, h->ev_deemph[b], 0));
+    return FMB_OK;
+}
+
+void *fmb_internal_stream(fmb_handle *h) { return h ? (void *) h->s_main : nullptr; }
+
+int fmb_sync(fmb_handle *h)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
     return FMB_OK;
 }
 
@@ -685,7 +767,11 @@ int fmb_set_state(fmb_handle *h, int first, int count, const fmb_stream_state *i
 {
     if (!h || !in || first < 0 || count < 0 || first + count > h->cfg.n_streams)
         return set_err(FMB_ERR_ARG, "bad state range");
-    if (prev_lpr_index < 0 || prev_lpr_index >= h->cfg.rate_in) return set_err(FMB_ERR_ARG, "bad prev_lpr_index");
+    if (prev_lpr_index < 0 || prev_lpr_index >= h->fast) return set_err(FMB_ERR_ARG, "bad prev_lpr_index");
+    {
+        const int rc = check_inplace_cycle(h, prev_lpr_index);
+        if (rc != FMB_OK) return rc;
+    }
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h->d_state[h->state_cur] + first, in, sizeof(fmb_stream_state) * (size_t) count, cudaMemcpyHostToDevice));

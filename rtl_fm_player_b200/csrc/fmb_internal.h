@@ -82,6 +82,9 @@ typedef struct fmb_dparams {
                                       were redone sequentially (diagnostic; may be NULL)   */
 } fmb_dparams;
 
+/* Sets fmb_last_error() of the calling thread (host code outside fmb_api.cu reports through it). */
+void fmb_set_last_error(const char *msg);
+
 /* Launchers (fmb_kernels.cu).  `stream` is a cudaStream_t.  Return cudaError_t as int. */
 int fmb_launch_demod(const fmb_config *cfg, const fmb_kparams *p, const fmb_tables *t, void *stream);
 int fmb_launch_deemph(const fmb_dparams *p, void *stream);

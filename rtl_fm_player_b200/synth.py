@@ -1,11 +1,35 @@
-"""Synthetic rtl_sdr-format captures (fmb_synth_capture, csrc/fm_synth.c)."""
+"""Synthetic rtl_sdr-format captures (include/fm_synth.h, csrc/fm_synth.c).
+
+Loads only rtl_fm_player_b200/libfmsynth.so (plain C, no CUDA): generating input data never maps the
+product library libfmb.so, so the reference arm of bench.py and the oracle tests stay free of it.
+Importable on its own path too (bench.py's reference arm loads this FILE without importing the package).
+"""
 from __future__ import annotations
 
+import ctypes as C
+import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from . import _lib as L
+SYNTH_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfmsynth.so")
+SYNTH_KINDS = {
+    "fm_stereo": 0, "fm_mono": 1, "random": 2, "const0": 3, "const127": 4, "const128": 5,
+    "const255": 6, "alt_0_255": 7, "impulse": 8, "carrier_off": 9,
+}
+_synth = None
+
+
+def synth_lib() -> C.CDLL:
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise FileNotFoundError(f"{SYNTH_LIB_PATH} not built; run `make -C rtl_fm_player_b200/csrc`")
+        lib = C.CDLL(SYNTH_LIB_PATH)
+        lib.fmb_synth_capture.restype = C.c_int
+        lib.fmb_synth_capture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+        _synth = lib
+    return _synth
 
 
 def capture(kind: str, stream: int, rate_in: int, offset_tuning: int, n_samples: int, first_sample: int = 0,
@@ -13,8 +37,9 @@ def capture(kind: str, stream: int, rate_in: int, offset_tuning: int, n_samples:
     """uint8 [2*n_samples] interleaved I,Q for one stream."""
     buf = np.empty(2 * n_samples, dtype=np.uint8) if out is None else out
     assert buf.dtype == np.uint8 and buf.size == 2 * n_samples and buf.flags.c_contiguous
-    L.check(L.lib().fmb_synth_capture(L.SYNTH_KINDS[kind], stream, rate_in, offset_tuning, first_sample, n_samples,
-                                      buf.ctypes.data), "fmb_synth_capture")
+    if synth_lib().fmb_synth_capture(SYNTH_KINDS[kind], stream, rate_in, offset_tuning, first_sample, n_samples,
+                                     buf.ctypes.data) != 0:
+        raise ValueError("fmb_synth_capture rejected its arguments")
     return buf
 
 

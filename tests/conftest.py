@@ -17,13 +17,18 @@ def pytest_sessionstart(session):
     __graft_entry__.build() does -- the CUDA library (nvcc cross-compiles without a GPU), the C restatement
     and, where /root/reference exists, the reference compiled from where it lies."""
     import subprocess
-    need = [os.path.join(ROOT, "rtl_fm_player_b200", "libfmb.so"), os.path.join(ROOT, "oracle", "libfm_oracle.so")]
+    need = [os.path.join(ROOT, "rtl_fm_player_b200", "libfmb.so"), os.path.join(ROOT, "rtl_fm_player_b200", "libfmsynth.so"),
+            os.path.join(ROOT, "oracle", "libfm_oracle.so")]
     if os.path.exists("/root/reference/src/rtl_fm_player.c"):
         need.append(os.path.join(ROOT, "oracle", "_ref", "libfmref.so"))
     if all(os.path.exists(f) for f in need):
         return
-    subprocess.run(["make", "-C", os.path.join(ROOT, "rtl_fm_player_b200", "csrc"), "-j4"], capture_output=True)
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port", "ref"], capture_output=True)
+    for cmd in (["make", "-C", os.path.join(ROOT, "rtl_fm_player_b200", "csrc"), "-j4"],
+                ["make", "-C", os.path.join(ROOT, "oracle"), "port", "ref"]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.exit("building the test artefacts failed: " + " ".join(cmd) + "\n" + r.stdout[-3000:] + r.stderr[-3000:],
+                        returncode=3)
 
 
 def _have_gpu() -> bool:

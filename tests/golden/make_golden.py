@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle.oracle_py import RefOracle  # noqa: E402
-from vectors import B, CASES, CONFIGS, LONG_CASES, make_input, sha  # noqa: E402
+from vectors import B, CASES, CONFIGS, LONG_CASES, long_capture_bytes, make_input, sha  # noqa: E402
 
 arrays, meta = {}, {"cases": {}, "long": {}, "tables": {}, "layout": {}}
 for cid, cfg, kind, stream, blocks in CASES:
@@ -32,8 +32,9 @@ for cid, cfg, kind, stream, blocks in CASES:
 
 for cid, cfg, kind, stream, blocks in LONG_CASES:
     iq = make_input(cfg, kind, stream, blocks)
-    # the 10 s capture is 30 720 000 bytes: the 49 152-byte tail is never demodulated (:863-868)
-    tail = np.zeros(30720000 - blocks * B, dtype=np.uint8)
+    # the 10 s capture is 30 720 000 bytes (192 k) / 38 400 000 (240 k): the tail short of a block is never demodulated (:863-868)
+    tail = np.zeros(long_capture_bytes(cfg) - blocks * B, dtype=np.uint8)
+    assert 0 <= tail.size < B
     pcm = RefOracle(**CONFIGS[cfg]).run(np.concatenate([iq, tail]))
     meta["long"][cid] = {"config": cfg, "kind": kind, "stream": stream, "blocks": blocks, "input_sha256": sha(iq),
                          "n_pcm": int(pcm.size), "pcm_sha256": sha(pcm)}

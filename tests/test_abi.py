@@ -20,9 +20,14 @@ GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
 META = json.load(open(os.path.join(HERE, "golden", "golden_meta.json")))
 
 
-def declared_symbols():
+SYNTH_HEADER = "fm_synth.h"        # its symbols live in libfmsynth.so (plain C), everything else in libfmb.so
+
+
+def declared_symbols(synth: bool = False):
     names = set()
     for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        if (os.path.basename(h) == SYNTH_HEADER) != synth:
+            continue
         src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
         src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src):
@@ -42,6 +47,28 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(syms) >= 50 and DROPIN <= set(syms)
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, f"declared in include/*.h but not exported: {missing}"
+    slib = C.CDLL(R.synth.SYNTH_LIB_PATH)
+    assert declared_symbols(synth=True) == ["fmb_synth_capture"] and hasattr(slib, "fmb_synth_capture")
+    assert not hasattr(lib, "fmb_synth_capture"), "the capture generator must stay out of the product library"
+
+
+def test_synth_library_is_plain_c_and_generating_data_does_not_map_the_product_library():
+    """bench.py's reference arm and the oracle legs only need input data: producing it must not load libfmb.so
+    (a reference-arm process that maps the product library voids the ratio)."""
+    import subprocess
+    import sys
+    needed = subprocess.run(["readelf", "-d", R.synth.SYNTH_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda" not in needed and "libcudart" not in needed and "libfmb" not in needed
+    code = ("import importlib.util, sys\n"
+            f"spec = importlib.util.spec_from_file_location('fm_synth_only', {os.path.join(ROOT, 'rtl_fm_player_b200', 'synth.py')!r})\n"
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+            "iq = m.capture('fm_stereo', 3, 192000, 0, 4096)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libfmsynth.so' in maps and 'libfmb.so' not in maps and 'libcudart' not in maps, maps\n"
+            "print(int(iq.sum()))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert int(r.stdout) == int(R.synth.capture("fm_stereo", 3, 192000, 0, 4096).sum())
 
 
 def test_python_binding_covers_fmb_h():
@@ -136,3 +163,24 @@ def test_synth_is_deterministic_and_piecewise_consistent():
 def test_synth_reproduces_golden_input_bytes():
     for cid, cfg, kind, stream, blocks in CASES[:4]:
         assert sha(make_input(cfg, kind, stream, blocks)) == META["cases"][cid]["input_sha256"]
+
+
+def test_device_list_parser_and_multi_create_without_a_device():
+    """fmb_multi.h host logic that needs no GPU: "-d 0-3,6" syntax; creating shards without a CUDA device
+    fails as a whole with FMB_ERR_CUDA (no CPU fallback) and the failing shard is named."""
+    assert R.parse_device_list("0-3,6") == [0, 1, 2, 3, 6]
+    assert R.parse_device_list("7") == [7]
+    assert R.parse_device_list("0,0") == [0, 0]
+    for bad in ("", "a", "1-", "3-1", "0,,1", "0,", "-1", "0-99999"):
+        with pytest.raises(R.FmbError) as e:
+            R.parse_device_list(bad)
+        assert e.value.code == L.FMB_ERR_ARG, bad
+    import torch
+    if not torch.cuda.is_available():
+        assert R.device_count() == 0
+        with pytest.raises(R.FmbError) as e:
+            R.FmMulti(R.DemodConfig.stereo_192k(n_streams=8), [0, 1])
+        assert e.value.code == L.FMB_ERR_CUDA and "shard" in str(e.value)
+    with pytest.raises(R.FmbError) as e:
+        R.FmMulti(R.DemodConfig.stereo_192k(n_streams=1), [0, 1])
+    assert e.value.code == L.FMB_ERR_ARG

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(HERE)
 
 class RefCfg(C.Structure):
     _fields_ = [("rate_in", C.c_int), ("rate_out2", C.c_int), ("mode", C.c_int), ("size", C.c_int),
-                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float)]
+                ("offset_tuning", C.c_int), ("deemph", C.c_double), ("volume", C.c_float), ("rate_out", C.c_int)]
 
 
 def layout():
@@ -60,7 +60,7 @@ def libs():
 def new_ref(ref, cfgname, **over):
     kw = dict(CONFIGS[cfgname]); kw.update(over)
     c = RefCfg(kw["rate_in"], kw["rate_out2"], kw["mode"], kw["size"], kw.get("offset_tuning", 0),
-               kw.get("deemph", 0.000050), kw.get("volume", 0.4))
+               kw.get("deemph", 0.000050), kw.get("volume", 0.4), kw.get("rate_out", 0))
     h = ref.ref_create(C.byref(c))
     assert h
     return h, ref.ref_demod_state(h)
@@ -106,7 +106,10 @@ def ref_block(ref, h, iq):
 
 @pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("stereo240", "random"), ("mono192", "fm_mono"),
                                           ("stereo192_off", "random"), ("mono240_off", "fm_mono"), ("drop192", "fm_stereo"),
-                                          ("nolpr192", "random"), ("nodeemph192", "random")])
+                                          ("nolpr192", "random"), ("nodeemph192", "random"),
+                                          # -o 2: the struct has rate_in = 2*rate_out (main :1510); lp_real_f32 ticks
+                                          # at rate_out (:485) while the filters follow rate_in
+                                          ("stereo384_o2", "fm_stereo"), ("stereo480_o2", "random")])
 def test_full_demod_on_the_references_struct_is_bit_identical(libs, cfgname, kind):
     ref, ours = libs
     kw = CONFIGS[cfgname]
@@ -132,6 +135,32 @@ def test_full_demod_on_the_references_struct_is_bit_identical(libs, cfgname, kin
             assert np.array_equal(ours_block(ours, d_gpu, blk, off), ref_block(ref, h_ref, blk)), f"block {b}"
         assert ours.fm_dropin_export_state(d_gpu) == 0
         assert state_bytes(d_gpu, mode) == state_bytes(d_ref, mode)
+    finally:
+        ours.fm_dropin_release(d_gpu)
+        ref.ref_destroy(h_ref)
+        ref.ref_destroy(h_gpu)
+
+
+def test_init_lp_real_f32_again_restarts_the_gpu_history(libs):
+    """The reference's init_lp_real_f32 callocs fresh rings (:430-436); called again on a struct that already has
+    a GPU context, ours must forget the GPU copy of the history too."""
+    ref, ours = libs
+    iq = make_input("stereo192", "random", 5, 2)
+    h_ref, d_ref = new_ref(ref, "stereo192")
+    h_gpu, d_gpu = new_ref(ref, "stereo192")
+    try:
+        blk = iq[:B]
+        assert np.array_equal(ours_block(ours, d_gpu, blk, 0), ref_block(ref, h_ref, blk))
+        # both sides re-init WITHOUT deinit (leaks the old rings, as the reference would): rings zeroed, pos 0,
+        # pp 0, everything else (lowpass_tb, pre_*, de-emphasis, resampler phase) carried on
+        ours.init_lp_real_f32(d_gpu)
+        ref2 = C.CDLL(REF_PATH)
+        if not hasattr(ref2, "ref_init_lp_real"):
+            pytest.skip("reference harness without the re-init hook")
+        ref2.ref_init_lp_real.argtypes = [C.c_void_p]
+        ref2.ref_init_lp_real(h_ref)
+        blk = iq[B:2 * B]
+        assert np.array_equal(ours_block(ours, d_gpu, blk, 0), ref_block(ref, h_ref, blk))
     finally:
         ours.fm_dropin_release(d_gpu)
         ref.ref_destroy(h_ref)

@@ -11,7 +11,7 @@ import pytest
 import rtl_fm_player_b200 as R
 from oracle.oracle_py import PortOracle
 from rtl_fm_player_b200 import _lib as L
-from vectors import B, CASES, CONFIGS, LONG_CASES, make_input, sha
+from vectors import B, CASES, CONFIGS, LONG_CASES, REFUSED, long_capture_bytes, make_input, sha
 
 pytestmark = pytest.mark.gpu
 
@@ -24,9 +24,17 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-def same_floats(a, b):
-    """bit-identical, or identical up to the sign of zero (which no later stage can observe)."""
-    return np.array_equal(bits(a), bits(b)) or np.array_equal(np.asarray(a), np.asarray(b))
+# Stage outputs are compared BIT for bit.  The only leniency is the sign of an exact zero, and only for the vectors
+# named here (digital silence / constant input, where the reference's early-return guards at :611-618 and :474 and
+# our branch-free forms may disagree on -0.0 vs +0.0 in a value that no later stage can observe; the PCM is
+# compared exactly everywhere).
+SIGNED_ZERO_CASES = set()
+
+
+def same_floats(a, b, cid=None):
+    if np.array_equal(bits(a), bits(b)):
+        return True
+    return cid in SIGNED_ZERO_CASES and np.array_equal(np.asarray(a), np.asarray(b))
 
 
 def cfg_for(name, **kw):
@@ -50,8 +58,8 @@ def test_cuda_pcm_equals_reference_golden_and_oracle_stages(case):
             pcm = fb.process(blk)
             dem, lr = fb.debug_read()
             p_or, st = port.block(blk[0], stages=True)
-            assert same_floats(dem[0], st["dem"]), f"block {b}: discriminator output differs"
-            assert same_floats(lr[0, :len(st["lr"])], st["lr"]), f"block {b}: decoder output differs"
+            assert same_floats(dem[0], st["dem"], cid), f"block {b}: discriminator output differs"
+            assert same_floats(lr[0, :len(st["lr"])], st["lr"], cid), f"block {b}: decoder output differs"
             assert np.array_equal(pcm[0], p_or), f"block {b}: PCM differs from the oracle"
             got.append(pcm[0])
     assert np.array_equal(np.concatenate(got), GOLD[cid]), "PCM differs from the reference's own output"
@@ -60,23 +68,39 @@ def test_cuda_pcm_equals_reference_golden_and_oracle_stages(case):
 @pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
 def test_configs_0_and_1_ten_second_capture(case):
     """BASELINE.json configs[0] (mono) and [1] (stereo): 10 s single-channel capture, sha256 of the
-    PCM must equal the reference's."""
+    PCM must equal the reference's.  configs[0] also at the literal default rate (rate_in 240 000 =
+    DEFAULT_SAMPLE_RATE h:30, rotate path): 38 400 000 bytes, 146 full blocks."""
     cid, cfg, kind, stream, blocks = case
     iq = make_input(cfg, kind, stream, blocks)
     m = META["long"][cid]
     with R.FmBatch(cfg_for(cfg, n_streams=1)) as fb:
-        pcm = fb.run(np.concatenate([iq, np.zeros(30720000 - blocks * B, np.uint8)])[None, :])
+        pcm = fb.run(np.concatenate([iq, np.zeros(long_capture_bytes(cfg) - blocks * B, np.uint8)])[None, :])
     assert pcm.shape[1] == m["n_pcm"] and sha(pcm[0]) == m["pcm_sha256"]
 
 
-def test_config_2_sixty_four_streams_each_vs_its_own_oracle():
-    n, blocks = 64, 3
+def test_config_2_sixty_four_streams_forty_blocks_each_vs_its_own_oracle():
+    """BASELINE.json configs[2] at the depth SURVEY s8d asks for: 64 distinct stereo channels x 40 block-steps
+    (16 MiB per step, 640 MiB in all), every channel's whole PCM against its own oracle run."""
+    from concurrent.futures import ThreadPoolExecutor
+    n, blocks = 64, 40
     kw = CONFIGS["stereo192"]
-    iq = R.synth.batch("fm_stereo", n, 192000, 0, blocks * B // 2)
+    iq = R.synth.batch("fm_stereo", n, 192000, 0, blocks * B // 2, threads=min(16, os.cpu_count() or 1))
     with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
         pcm = fb.run(iq)
+        assert fb.deemph_fallbacks() < n * blocks       # the speculative IIR verified nearly everywhere
+    assert pcm.shape == (n, blocks * 8192)
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:   # ctypes releases the GIL
+        want = list(ex.map(lambda s: PortOracle(**kw).run(iq[s]), range(n)))
     for s in range(n):
-        assert np.array_equal(pcm[s], PortOracle(**kw).run(iq[s])), f"stream {s}"
+        assert np.array_equal(pcm[s], want[s]), f"stream {s}"
+
+
+def test_oracle_on_this_box_still_matches_the_reference_golden_pcm():
+    """The oracle libraries on the GPU box are the prebuilt ones: re-pin them here, in the -m gpu session too."""
+    for cid, cfg, kind, stream, blocks in CASES:
+        iq = make_input(cfg, kind, stream, blocks)
+        assert sha(iq) == META["cases"][cid]["input_sha256"]
+        assert np.array_equal(PortOracle(**CONFIGS[cfg]).run(iq), GOLD[cid]), cid
 
 
 @pytest.mark.parametrize("segs", [1, 2, 4, 8])
@@ -91,9 +115,10 @@ def test_time_segmentation_does_not_change_the_result(cfgname, kind, segs):
 
 
 @pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("stereo192", "random"), ("mono192", "random"),
-                                          ("stereo240", "fm_stereo")])
+                                          ("stereo240", "fm_stereo"), ("stereo170_44", "fm_stereo"),
+                                          ("stereo170_44", "random"), ("mono240_32", "fm_mono"), ("mono240", "random")])
 def test_fma_precision_within_one_lsb(cfgname, kind):
-    blocks = 6 if cfgname == "stereo240" else 3
+    blocks = 6 if cfgname in ("stereo240", "stereo170_44", "mono240_32", "mono240") else 3
     iq = make_input(cfgname, kind, 3, blocks)[None, :]
     with R.FmBatch(cfg_for(cfgname, n_streams=1, precision=R.FMB_PRECISION_FMA)) as fb:
         pcm = fb.run(iq)[0].astype(np.int32)
@@ -248,22 +273,64 @@ def test_kernels_really_launch_and_errors_are_loud():
         rc = fb._lib.fmb_process(fb._h, iq.ctypes.data, B, pcm.ctypes.data, 16, None)
         assert rc == L.FMB_ERR_ARG                       # pcm_pitch < out count
         assert fb._lib.fmb_wait(fb._h, 12345, None) == L.FMB_ERR_STATE
-    # rate ratio < 3 with a resampler phase where the reference's in-place stereo output would
-    # overwrite unread input beyond the emulated first-sample case: refused, never silently wrong
-    with R.FmBatch(cfg_for("stereo192", n_streams=1, rate_in=100000)) as fb:
-        st, _, _ = fb.get_state()
-        fb.set_state(st, 60000, 0)
+
+
+def test_inplace_hazard_is_refused_at_create_not_in_the_middle_of_playback():
+    """A stereo rate ratio between 2 and 3 whose block-start phases reach a tick on sample <= 2 would make the
+    reference's in-place output overwrite unread input beyond the emulated first-sample case (:593-597).
+    100000/48000 does so on its third block (phase 64000): refused by fmb_create, and by fmb_set_state for an
+    imported phase -- never silently wrong, never an abort after two good blocks."""
+    for name, kw in REFUSED.items():
         with pytest.raises(R.FmbError) as e:
-            fb.process(iq)
+            R.FmBatch(R.DemodConfig(n_streams=1, **kw))
+        assert e.value.code == L.FMB_ERR_UNSUPPORTED, name
+    # ratio 2.67: 16384*48000 is a multiple of 128000, every block starts at phase 0: fine; an imported phase of
+    # 120000 >= 2*128000 - 3*48000 puts tick 1 on sample 2: refused
+    kw = dict(CONFIGS["stereo192"], rate_in=128000)
+    iq = make_input("stereo192", "random", 1, 2)
+    with R.FmBatch(R.DemodConfig(n_streams=1, **kw)) as fb:
+        pcm = fb.run(iq[None, :])
+        assert np.array_equal(pcm[0], PortOracle(**kw).run(iq))
+        st, _, _ = fb.get_state()
+        with pytest.raises(R.FmbError) as e:
+            fb.set_state(st, 120000, 0)
         assert e.value.code == L.FMB_ERR_UNSUPPORTED
 
 
-def test_low_rate_ratio_supported_where_hazard_free():
-    iq = make_input("stereo192", "random", 1, 1)[None, :]
-    kw = dict(CONFIGS["stereo192"], rate_in=100000)
-    with R.FmBatch(R.DemodConfig(n_streams=1, **kw)) as fb:
-        pcm = fb.process(iq)
-    assert np.array_equal(pcm[0], PortOracle(**kw).run(iq[0]))
+def test_caller_may_alternate_cuda_streams_between_steps():
+    """fmb_process_device on a different stream than the previous step first waits (device side) for that
+    step's demodulation: the carried state ping-pongs between the two calls.  Alternating two streams, with no
+    host synchronisation in between, must still give the oracle's PCM."""
+    import torch
+    n, blocks = 96, 6
+    uniq = 4
+    iq = np.stack([make_input("stereo192", "fm_stereo", s % uniq, blocks) for s in range(n)])
+    want = [PortOracle(**CONFIGS["stereo192"]).run(iq[s]) for s in range(uniq)]
+    d_in = torch.from_numpy(iq).cuda()
+    d_out = torch.zeros((blocks, n, 8192), dtype=torch.int16, device="cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb:
+        for b in range(blocks):
+            fb.process_device(d_in.data_ptr() + b * B, iq.shape[1], d_out[b].data_ptr(), 8192, streams[b & 1].cuda_stream)
+        for st in streams:
+            fb.join(st.cuda_stream)
+        torch.cuda.synchronize()
+    got = np.concatenate([d_out[b].cpu().numpy() for b in range(blocks)], axis=1)
+    for s in range(n):
+        assert np.array_equal(got[s], want[s % uniq]), s
+
+
+def test_rate_out_below_rate_in_follows_the_reference():
+    """-o 2 configurations (filters at rate_in, ticks at rate_out) across carried blocks, several channels."""
+    for name, kind in (("stereo384_o2", "random"), ("stereo480_o2", "fm_stereo"), ("mono384_o2", "random")):
+        kw = CONFIGS[name]
+        blocks = 6 if name == "stereo480_o2" else 2
+        iq = np.stack([make_input(name, kind, s, blocks) for s in range(3)])
+        with R.FmBatch(cfg_for(name, n_streams=3)) as fb:
+            pcm = fb.run(iq)
+        for s in range(3):
+            assert np.array_equal(pcm[s], PortOracle(**kw).run(iq[s])), (name, s)
 
 
 def test_deemphasis_speculation_is_verified_and_falls_back_on_digital_silence():

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle_py import PortOracle, RefOracle, ref_available
-from vectors import B, CASES, CONFIGS, LONG_CASES, make_input, sha
+from vectors import B, CASES, CONFIGS, LONG_CASES, long_capture_bytes, make_input, sha
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
@@ -60,13 +60,14 @@ def test_reference_stage_calls_equal_full_demod():
 
 @pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
 def test_port_long_capture_configs_0_and_1(case):
-    """BASELINE.json configs[0]/[1]: 10 s single-channel captures, 117 full blocks."""
+    """BASELINE.json configs[0]/[1]: 10 s single-channel captures, 117 full blocks at 8 x 192 kHz; configs[0] also at
+    the literal default rate (8 x 240 kHz, rotate path): 146 full blocks."""
     cid, cfg, kind, stream, blocks = case
     iq = make_input(cfg, kind, stream, blocks)
     m = META["long"][cid]
     assert sha(iq) == m["input_sha256"]
-    pcm = PortOracle(**CONFIGS[cfg]).run(np.concatenate([iq, np.zeros(30720000 - blocks * B, np.uint8)]))
-    assert pcm.size == m["n_pcm"]          # the 49 152-byte tail is dropped (:863-868)
+    pcm = PortOracle(**CONFIGS[cfg]).run(np.concatenate([iq, np.zeros(long_capture_bytes(cfg) - blocks * B, np.uint8)]))
+    assert pcm.size == m["n_pcm"]          # the tail short of a block (49 152 B at 192 k) is dropped (:863-868)
     assert sha(pcm) == m["pcm_sha256"]
 
 
@@ -86,6 +87,19 @@ def test_known_constants_from_survey():
     m = PortOracle(rate_in=240000, mode=2, size=90).tables()["misc"]
     assert abs(m[0] - 0.47715878) < 1e-7 and abs(m[1] - 0.8788171) < 1e-7
     assert m[3] == np.float32(0.4) * np.float32(32768.0)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_rate_out_differs_from_rate_in_under_post_downsample():
+    """-o N: main does rate_in *= post_downsample (:1510) and leaves rate_out, so the filters are designed for
+    rate_in while lp_real_f32's ticks run at rate_out/rate_out2 (:485).  The port follows the reference there,
+    and the result is NOT what rate_out = rate_in would give."""
+    kw = CONFIGS["stereo384_o2"]
+    iq = make_input("stereo384_o2", "fm_stereo", 1, 2)
+    a = RefOracle(**kw).run(iq)
+    assert np.array_equal(a, PortOracle(**kw).run(iq))
+    same_rate = dict(kw, rate_out=0)
+    assert PortOracle(**same_rate).run(iq).size != a.size     # 8 ticks per 64 samples instead of 16
 
 
 def test_block_split_invariance_when_no_quirk():

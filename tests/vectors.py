@@ -27,8 +27,17 @@ CONFIGS = {
     "stereo256_48": dict(rate_in=256000, rate_out2=48000, mode=2, size=90, offset_tuning=1),
     "mono240_32": dict(rate_in=240000, rate_out2=32000, mode=1, size=128, offset_tuning=0),
     "stereo192_us": dict(rate_in=192000, rate_out2=48000, mode=2, size=90, offset_tuning=0, deemph=0.000075),
-    "stereo100_48": dict(rate_in=100000, rate_out2=48000, mode=2, size=90, offset_tuning=0),  # ratio 2.08
+    "stereo96_48": dict(rate_in=96000, rate_out2=48000, mode=2, size=90, offset_tuning=0),    # ratio 2: the lowest stereo allows
+    # the literal defaults of demod_init with -Y's decoder: mono at DEFAULT_SAMPLE_RATE (h:30), rotate path
+    "mono240": dict(rate_in=240000, rate_out2=48000, mode=1, size=128, offset_tuning=0),
+    "mono240_loud": dict(rate_in=240000, rate_out2=48000, mode=1, size=128, offset_tuning=0, volume=1.5),
+    # -o 2 (main: rate_in *= post_downsample, :1510): filters designed for rate_in, resampler ticks at rate_out (:485)
+    "stereo384_o2": dict(rate_in=384000, rate_out=192000, rate_out2=48000, mode=2, size=90, offset_tuning=0),
+    "stereo480_o2": dict(rate_in=480000, rate_out=240000, rate_out2=48000, mode=2, size=90, offset_tuning=0),  # + Q1 quirk
+    "mono384_o2": dict(rate_in=384000, rate_out=192000, rate_out2=48000, mode=1, size=128, offset_tuning=1),
 }
+# ratios between 2 and 3 whose block-start phases reach the reference's unemulated in-place overwrite: refused at create
+REFUSED = {"stereo100_48": dict(rate_in=100000, rate_out2=48000, mode=2, size=90, offset_tuning=0)}
 
 # (case id, config, synth kind, stream id, blocks)
 CASES = [
@@ -60,15 +69,29 @@ CASES = [
     ("stereo256_48_random", "stereo256_48", "random", 11, 5),
     ("mono240_32_fm", "mono240_32", "fm_mono", 2, 4),
     ("stereo192_us_fm", "stereo192_us", "fm_stereo", 5, 3),
-    ("stereo100_48_random", "stereo100_48", "random", 12, 2),
+    ("stereo96_48_random", "stereo96_48", "random", 12, 3),
+    ("mono192_carrier", "mono192", "carrier_off", 0, 3),         # mono saturation (clamp at :722-729)
+    ("mono240_fm", "mono240", "fm_mono", 3, 6),
+    ("mono240_loud_random", "mono240_loud", "random", 1, 3),     # saturation on the generic tick path
+    ("stereo384_o2_fm", "stereo384_o2", "fm_stereo", 6, 3),
+    ("stereo480_o2_random", "stereo480_o2", "random", 13, 7),
+    ("mono384_o2_fm", "mono384_o2", "fm_mono", 4, 3),
 ]
 CASE_BY_ID = {c[0]: c for c in CASES}
 
-# full-length cases of BASELINE.json configs[0]/[1]: 10 s captures, 117 full blocks; golden = sha256 of the PCM
+# full-length cases of BASELINE.json configs[0]/[1]: 10 s captures; golden = sha256 of the PCM.  (id, config, kind,
+# stream, full blocks): 10 s at 8*192 kHz = 30 720 000 B = 117 blocks + a tail that is never demodulated (:863-868);
+# at the literal default rate 8*240 kHz = 38 400 000 B = 146 blocks + tail.
 LONG_CASES = [
     ("c1_mono192_10s", "mono192", "fm_mono", 0, 117),
     ("c2_stereo192_10s", "stereo192", "fm_stereo", 0, 117),
+    ("c0_mono240_10s", "mono240", "fm_mono", 0, 146),
 ]
+
+
+def long_capture_bytes(cfg_name: str) -> int:
+    """10 s of capture at 8 x rate_in, 2 bytes per IQ sample."""
+    return 10 * 8 * CONFIGS[cfg_name]["rate_in"] * 2
 
 
 def make_input(cfg_name: str, kind: str, stream: int, blocks: int) -> np.ndarray:
