@@ -27,7 +27,7 @@ static_assert(offsetof(fmb_stream_state, raw_tail) % 16 == 0 && sizeof(fmb_strea
 
 namespace {
 
-constexpr int kLrBufs = 3;
+constexpr int kLrBufs = FMB_LR_BUFS;
 
 thread_local char g_err[512] = "";
 std::atomic<long> g_launches{0};
@@ -66,8 +66,15 @@ struct fmb_handle {
     int grid;                  /* CTAs of the demod kernel */
     int ctas_per_sm = 0;       /* > 0 when the grid is exactly one full wave (SMs x occupancy) */
     int chunk = 0, n_whole = 0; /* dynamic work assignment of the demod kernel (0 = static), see fmb_kparams */
-    unsigned int *d_tickets = nullptr;
-    unsigned int ticket_base = 0;
+    unsigned int *d_tickets = nullptr;         /* FMB_TICKET_SLOTS counters, used in rotation by launch sequence number */
+    unsigned int ticket_base[FMB_TICKET_SLOTS] = {};
+    /* overlap of consecutive demod launches (programmatic dependent launch, see fmb_kparams.done) */
+    unsigned int *d_done = nullptr;            /* [n_streams] stream hand-over counters */
+    unsigned int *d_de_done = nullptr;         /* [n_streams] de-emphasis passes completed */
+    unsigned int *d_err = nullptr;             /* device error word (flag wait timed out) */
+    unsigned int *h_err = nullptr;             /* pinned copy, refreshed by the host path's D2H stream */
+    unsigned int seq = 0;                      /* sequence number of the next demod launch (never reset) */
+    int pdl = 1;
     int max_out;
     /* resampler bookkeeping (common to all streams) */
     int phase;                 /* prev_lpr_index */
@@ -223,6 +230,16 @@ int fold_profile(fmb_handle *h)
     return FMB_OK;
 }
 
+/* The kernels never spin without a bound; if a stream hand-over wait ever timed out (a logic error), results are
+ * void: say so loudly.  Call after a device synchronisation. */
+int check_device_error(fmb_handle *h)
+{
+    unsigned int v = 0;
+    CU(cudaMemcpy(&v, h->d_err, sizeof v, cudaMemcpyDeviceToHost));
+    if (v) { h->poisoned = true; return set_err(FMB_ERR_STATE, "device-side stream hand-over wait timed out: results are invalid"); }
+    return FMB_OK;
+}
+
 /* Enqueue one block-step: demod kernel on `sm`, de-emphasis kernel on the aux
  * stream.  d_iq/d_pcm are device pointers. */
 int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d_pcm, size_t pcm_pitch,
@@ -244,8 +261,11 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
      * handle; these waits come first and change nothing if they fail. */
     /* a different caller stream than last time: order this step behind the previous step's demod kernel */
     if (h->have_last_stream && h->last_stream != sm) CU(cudaStreamWaitEvent(sm, h->ev_demod[h->last_lr], 0));
-    /* the de-emphasis pass that last read d_lr[b] must be done before we overwrite it */
-    if (h->deemph_pending[b]) CU(cudaStreamWaitEvent(sm, h->ev_deemph[b], 0));
+    /* The de-emphasis pass that last read d_lr[b] (FMB_LR_BUFS steps ago) must be done with a stream's row before this
+     * launch overwrites it.  With overlapping launches that is ordered per stream inside the kernel (de_done, see
+     * wait_stream) and NO stream operation is put between this launch and the previous one -- a cross-stream wait
+     * here would serialise them again.  Without overlap the event does it. */
+    if (h->deemph_pending[b] && !h->pdl) CU(cudaStreamWaitEvent(sm, h->ev_deemph[b], 0));
 
     fmb_kparams kp;
     memset(&kp, 0, sizeof kp);
@@ -275,10 +295,16 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
         const int spb = h->n_dem / FMB_NSUB;
         kp.chunk = h->chunk;
         kp.n_whole = h->n_whole;
-        kp.tickets = h->d_tickets;
-        kp.ticket_base = h->ticket_base;
+        kp.tickets = h->d_tickets + (h->seq % FMB_TICKET_SLOTS);
+        kp.ticket_base = h->ticket_base[h->seq % FMB_TICKET_SLOTS];
         ticket_step = (unsigned int) (h->n_whole + (c.n_streams - h->n_whole) * (spb / h->chunk) + h->grid);
     }
+
+    kp.done = h->d_done;
+    kp.de_done = h->d_de_done;
+    kp.seq = h->seq;
+    kp.dev_err = h->d_err;
+    kp.pdl = h->pdl;
 
     fmb_config kc = c;
     if (c.rate_out2 <= 0) kc.mode = 0;
@@ -313,6 +339,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     dp.lambda = h->tab.lambda;
     dp.pcm_scale = h->tab.pcm_scale;
     dp.fallbacks = h->d_fallbacks;
+    dp.de_done = h->d_de_done;
     if (prof) CUP(cudaEventRecord(h->pev[1][0][h->pcount[1]], h->s_aux));
 #ifdef FMB_TUNE_SKIP_DEEMPH   /* tools/build_variant.sh only: timing experiment, PCM is not produced */
     e = cudaSuccess;
@@ -325,7 +352,8 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     CUP(cudaEventRecord(h->ev_deemph[b], h->s_aux));
 #undef CUP
     h->deemph_pending[b] = true;
-    h->ticket_base += ticket_step;
+    h->ticket_base[h->seq % FMB_TICKET_SLOTS] += ticket_step;
+    h->seq++;
     h->last_stream = sm;
     h->have_last_stream = true;
 
@@ -486,8 +514,21 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
     CUH(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) cfg->n_streams));
     CUH(cudaMalloc(&h->d_fallbacks, sizeof(unsigned int)));
     CUH(cudaMemset(h->d_fallbacks, 0, sizeof(unsigned int)));
-    CUH(cudaMalloc(&h->d_tickets, sizeof(unsigned int)));
-    CUH(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
+    CUH(cudaMalloc(&h->d_tickets, sizeof(unsigned int) * FMB_TICKET_SLOTS));
+    CUH(cudaMemset(h->d_tickets, 0, sizeof(unsigned int) * FMB_TICKET_SLOTS));
+    CUH(cudaMalloc(&h->d_done, sizeof(unsigned int) * (size_t) cfg->n_streams));
+    CUH(cudaMemset(h->d_done, 0, sizeof(unsigned int) * (size_t) cfg->n_streams));
+    CUH(cudaMalloc(&h->d_de_done, sizeof(unsigned int) * (size_t) cfg->n_streams));
+    CUH(cudaMemset(h->d_de_done, 0, sizeof(unsigned int) * (size_t) cfg->n_streams));
+    CUH(cudaMalloc(&h->d_err, sizeof(unsigned int)));
+    CUH(cudaMemset(h->d_err, 0, sizeof(unsigned int)));
+    CUH(cudaHostAlloc((void **) &h->h_err, sizeof(unsigned int), cudaHostAllocDefault));
+    *h->h_err = 0;
+    {
+        /* FMB_PDL=0: plain stream order between consecutive demod launches (tuning / A-B comparison) */
+        const char *ep = getenv("FMB_PDL");
+        h->pdl = (ep && atoi(ep) == 0) ? 0 : 1;
+    }
     {
         /* Dynamic work assignment (see fmb_demod_kernel).  It pays when every CTA of the resident wave has
          * several streams' worth of work: whole streams first, and about FMB_DEFAULT_TAIL_RUNS fine-grain
@@ -507,6 +548,11 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
                 int tail = atoi(et);
                 tail = tail < 0 ? 0 : tail > 100 ? 100 : tail;
                 tail_streams = cfg->n_streams - (int) ((long long) cfg->n_streams * (100 - tail) / 100);
+            } else if (h->pdl) {
+                /* overlapping launches: the CTAs of the next launch take over the slots this launch's ragged end
+                 * frees, so nothing has to finish together -- every stream is handed out whole (no lead-ins to
+                 * recompute).  1024 streams: 0.3475 -> 0.3337 ms per step (profiles/r02g_pdl_tail_sweep.txt) */
+                tail_streams = 0;
             } else {
                 tail_streams = (FMB_DEFAULT_TAIL_RUNS * chunk * h->grid + spb - 1) / spb;
                 if (tail_streams > cfg->n_streams) tail_streams = cfg->n_streams;
@@ -547,6 +593,10 @@ int fmb_destroy(fmb_handle *h)
     if (h->d_de_state) cudaFree(h->d_de_state);
     if (h->d_fallbacks) cudaFree(h->d_fallbacks);
     if (h->d_tickets) cudaFree(h->d_tickets);
+    if (h->d_done) cudaFree(h->d_done);
+    if (h->d_de_done) cudaFree(h->d_de_done);
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->h_err) cudaFreeHost(h->h_err);
     if (h->d_dem) cudaFree(h->d_dem);
     for (auto &s : h->slot) {
         if (s.d_iq) cudaFree(s.d_iq);
@@ -582,8 +632,22 @@ int fmb_reset(fmb_handle *h)
     const size_t st_bytes = sizeof(fmb_stream_state) * (size_t) h->cfg.n_streams;
     for (int i = 0; i < 2; ++i) CU(cudaMemset(h->d_state[i], 0, st_bytes));
     CU(cudaMemset(h->d_de_state, 0, sizeof(float) * 2 * (size_t) h->cfg.n_streams));
-    CU(cudaMemset(h->d_tickets, 0, sizeof(unsigned int)));
-    h->ticket_base = 0;
+    /* The ticket counters run on.  The stream hand-over counters stand at 2*seq after a clean run (what the next
+     * launch waits for); they are set to that explicitly so that reset also recovers a handle whose flag wait timed
+     * out, and the error word is cleared. */
+    {
+        unsigned int *fill = (unsigned int *) malloc(sizeof(unsigned int) * (size_t) h->cfg.n_streams);
+        if (!fill) return set_err(FMB_ERR_NOMEM, "reset");
+        for (int i = 0; i < h->cfg.n_streams; ++i) fill[i] = 2u * h->seq;
+        cudaError_t e = cudaMemcpy(h->d_done, fill, sizeof(unsigned int) * (size_t) h->cfg.n_streams, cudaMemcpyHostToDevice);
+        for (int i = 0; i < h->cfg.n_streams; ++i) fill[i] = h->seq;
+        if (e == cudaSuccess)
+            e = cudaMemcpy(h->d_de_done, fill, sizeof(unsigned int) * (size_t) h->cfg.n_streams, cudaMemcpyHostToDevice);
+        free(fill);
+        if (e != cudaSuccess) return set_err(FMB_ERR_CUDA, "cudaMemcpy stream counters", e);
+        CU(cudaMemset(h->d_err, 0, sizeof(unsigned int)));
+        *h->h_err = 0;
+    }
     h->phase = 0;
     h->blocks_done = 0;
     h->poisoned = false;
@@ -619,7 +683,7 @@ int fmb_sync(fmb_handle *h)
     if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    return FMB_OK;
+    return check_device_error(h);
 }
 
 static int ensure_slots(fmb_handle *h)
@@ -665,6 +729,7 @@ int fmb_submit(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t *
     if (s.n_out > 0)
         CU(cudaMemcpy2DAsync(pcm_host, pcm_pitch * sizeof(int16_t), s.d_pcm, h->d_pcm_pitch * sizeof(int16_t),
                              (size_t) s.n_out * sizeof(int16_t), (size_t) c.n_streams, cudaMemcpyDeviceToHost, h->s_d2h));
+    CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
     CU(cudaEventRecord(s.ev_done, h->s_d2h));
     s.busy = true;
     h->next_ticket++;
@@ -681,6 +746,7 @@ int fmb_wait(fmb_handle *h, int ticket, int *n_out)
     if (!s.busy) return set_err(FMB_ERR_STATE, "ticket already waited for");
     CU(cudaEventSynchronize(s.ev_done));
     s.busy = false;
+    if (*h->h_err) { h->poisoned = true; return set_err(FMB_ERR_STATE, "device-side stream hand-over wait timed out: results are invalid"); }
     if (n_out)
         for (int i = 0; i < h->cfg.n_streams; ++i) n_out[i] = s.n_out;
     return FMB_OK;
@@ -751,6 +817,10 @@ int fmb_get_state(fmb_handle *h, int first, int count, fmb_stream_state *out, in
         return set_err(FMB_ERR_ARG, "bad state range");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
+    {
+        const int rc = check_device_error(h);
+        if (rc != FMB_OK) return rc;
+    }
     CU(cudaMemcpy(out, h->d_state[h->state_cur] + first, sizeof(fmb_stream_state) * (size_t) count, cudaMemcpyDeviceToHost));
     float *de = (float *) malloc(sizeof(float) * 2 * (size_t) (count ? count : 1));
     if (!de) return set_err(FMB_ERR_NOMEM, "state");

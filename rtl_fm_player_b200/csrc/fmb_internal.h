@@ -63,9 +63,24 @@ typedef struct fmb_kparams {
     /* Dynamic work assignment (chunk > 0): see "work assignment" in fmb_demod_kernel. */
     int chunk;                     /* units per fine-grain run; divides n_dem / FMB_NSUB  */
     int n_whole;                   /* streams handed out whole before the fine-grain runs */
-    unsigned int *tickets;         /* global ticket counter                               */
+    unsigned int *tickets;         /* global ticket counter (one of FMB_TICKET_SLOTS, by launch sequence number:
+                                      consecutive launches overlap at their ends and must not share one)        */
     unsigned int ticket_base;      /* its value when this launch starts                   */
+    /* Overlap of consecutive launches (programmatic dependent launch): the next launch's CTAs may start while this
+     * one's last CTAs are still running, so the only true dependency -- the carried state of a stream -- is ordered
+     * by a per-stream counter instead of the launch boundary.  Every launch adds two events to done[s]: st_in[s] has
+     * been read (end of the block's first sub-tile) and st_out[s] is complete (end of its last); launch q (q = 0, 1, ..)
+     * waits for done[s] >= 2q before a run touches stream s, i.e. until launch q-1 has both produced the state q reads
+     * and consumed the buffer q overwrites. */
+    unsigned int *done;            /* [n_streams]                                         */
+    const unsigned int *de_done;   /* [n_streams] de-emphasis passes completed per stream (fmb_dparams.de_done): launch q
+                                      overwrites the decoder-output buffer pass q - FMB_LR_BUFS read            */
+    unsigned int seq;              /* this launch's sequence number                       */
+    unsigned int *dev_err;         /* set to 1 if a flag wait ever times out (never hangs the GPU) */
+    int pdl;                       /* 1: release the dependent launch at kernel start (griddepcontrol.launch_dependents) */
 } fmb_kparams;
+#define FMB_TICKET_SLOTS 4
+#define FMB_LR_BUFS 3              /* decoder-output buffers in rotation (see fmb_handle.d_lr)                  */
 
 typedef struct fmb_dparams {
     const float *lr;
@@ -80,6 +95,7 @@ typedef struct fmb_dparams {
     float lambda, pcm_scale;
     unsigned int *fallbacks;       /* device counter: chunks whose time-speculation failed and
                                       were redone sequentially (diagnostic; may be NULL)   */
+    unsigned int *de_done;         /* [n_streams] += 1 when this pass is done with the stream's input row        */
 } fmb_dparams;
 
 /* Sets fmb_last_error() of the calling thread (host code outside fmb_api.cu reports through it). */

@@ -1,0 +1,14 @@
+#!/bin/bash
+# time tuning variants (tools/variants/libfmb_<name>.so) of the demod step: usage gpu_variants.sh <tag> <mode> <names...>
+TAG=$1; MODE=$2; shift 2
+mkdir -p gpurun_out
+{
+for n in "$@"; do
+  echo "== variant $n"
+  if [ "$n" = "main" ]; then timeout 200 python tools/sweep_env.py FMB_PDL $MODE 0 1
+  else FMB_LIB_PATH=$PWD/tools/variants/libfmb_$n.so timeout 200 python tools/sweep_env.py FMB_PDL $MODE 0 1; fi
+done
+echo "== main lib on a created stream"
+SWEEP_STREAM=1 timeout 200 python tools/sweep_env.py FMB_PDL $MODE 0 1 0 1
+} > gpurun_out/${TAG}_variants.txt 2>&1
+cat gpurun_out/${TAG}_variants.txt

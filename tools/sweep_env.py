@@ -19,6 +19,9 @@ for u in range(uniq):
 for s in range(uniq, S):
     host[:, s] = host[:, s % uniq]
 dev_in = [torch.from_numpy(host[b]).cuda() for b in range(NBUF)]
+if os.environ.get("SWEEP_STREAM", "0") == "1":      # a created (non-default) stream instead of torch's current (legacy default) one
+    _st = torch.cuda.Stream()
+    torch.cuda.set_stream(_st)
 stream = torch.cuda.current_stream().cuda_stream
 ref = None
 for v in vals:
