@@ -63,9 +63,14 @@ struct fmb_handle {
     fmb_config cfg;
     fmb_tables tab;
     int n_dem;                 /* demodulated samples per stream per step */
-    int grid;                  /* CTAs of the demod kernel */
-    int ctas_per_sm = 0;       /* > 0 when the grid is exactly one full wave (SMs x occupancy) */
-    int chunk = 0, n_whole = 0; /* dynamic work assignment of the demod kernel (0 = static), see fmb_kparams */
+    /* launch geometry and work-assignment policy of one demod kernel */
+    struct Plan {
+        int grid = 0;              /* CTAs */
+        int ctas_per_sm = 0;       /* > 0 when the grid is exactly one full wave (SMs x occupancy) */
+        int chunk = 0, n_whole = 0; /* dynamic work assignment (0 = static), see fmb_kparams */
+    };
+    Plan plan;                 /* fmb_demod_kernel */
+    Plan plan_ws;              /* the warp-specialised kernel of this configuration (grid 0: none) */
     unsigned int *d_tickets = nullptr;         /* FMB_TICKET_SLOTS counters, used in rotation by launch sequence number */
     unsigned int ticket_base[FMB_TICKET_SLOTS] = {};
     /* overlap of consecutive demod launches (programmatic dependent launch, see fmb_kparams.done) */
@@ -278,7 +283,13 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     kp.dem_dump = h->debug ? h->d_dem : nullptr;
     kp.dem_pitch = h->n_dem;
     kp.n_streams = c.n_streams;
-    kp.grid = h->grid;
+    /* which kernel: the warp-specialised one where this configuration has it and the resampler is on its 4:1 fast path */
+    const bool dec4 = c.rate_out2 > 0 && h->fast % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0 &&
+                      h->fast / c.rate_out2 == 4 && h->phase / c.rate_out2 == 0;
+    const bool ws = h->plan_ws.grid > 0 && dec4;
+    const fmb_handle::Plan &pl = ws ? h->plan_ws : h->plan;
+    kp.ws = ws ? 1 : 0;
+    kp.grid = pl.grid;
     kp.n_dem = h->n_dem;
     if (c.rate_out2 > 0) {
         kp.slow = c.rate_out2; kp.fast = h->fast; kp.phase0 = h->phase;
@@ -291,13 +302,13 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     }
     kp.quirk = quirk ? 1 : 0;
     unsigned int ticket_step = 0;      /* tickets this launch consumes; committed with the rest of the bookkeeping */
-    if (h->chunk > 0) {
+    if (pl.chunk > 0) {
         const int spb = h->n_dem / FMB_NSUB;
-        kp.chunk = h->chunk;
-        kp.n_whole = h->n_whole;
+        kp.chunk = pl.chunk;
+        kp.n_whole = pl.n_whole;
         kp.tickets = h->d_tickets + (h->seq % FMB_TICKET_SLOTS);
         kp.ticket_base = h->ticket_base[h->seq % FMB_TICKET_SLOTS];
-        ticket_step = (unsigned int) (h->n_whole + (c.n_streams - h->n_whole) * (spb / h->chunk) + h->grid);
+        ticket_step = (unsigned int) (pl.n_whole + (c.n_streams - pl.n_whole) * (spb / pl.chunk) + pl.grid);
     }
 
     kp.done = h->d_done;
@@ -467,11 +478,11 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
                 delete h;
                 return set_err(FMB_ERR_ARG, "segments must divide block_bytes/32768");
             }
-            h->grid = cfg->n_streams * cfg->segments;
+            h->plan.grid = cfg->n_streams * cfg->segments;
         } else {
             fmb_config kc = *cfg;
             if (cfg->rate_out2 <= 0) kc.mode = 0;
-            int occ = 0, sms = 0;
+            int occ = 0, occ_ws = 0, sms = 0;
             cudaError_t e1 = (cudaError_t) fmb_demod_occupancy(&kc, &occ);
             cudaError_t e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
             if (e1 != cudaSuccess || e2 != cudaSuccess || occ < 1 || sms < 1) {
@@ -479,8 +490,19 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
                 return set_err(FMB_ERR_CUDA, "occupancy query for the demod kernel", e1 != cudaSuccess ? e1 : e2);
             }
             const long long slots = (long long) occ * sms;
-            h->grid = (int) (units < slots ? units : slots);
-            if (units >= slots) h->ctas_per_sm = occ;
+            h->plan.grid = (int) (units < slots ? units : slots);
+            if (units >= slots) h->plan.ctas_per_sm = occ;
+            /* FMB_WS=0: never use the warp-specialised kernels (tuning / A-B comparison) */
+            const char *ew = getenv("FMB_WS");
+            if (!(ew && atoi(ew) == 0) && cfg->rate_out2 > 0) {
+                e1 = (cudaError_t) fmb_demod_ws_occupancy(&kc, &occ_ws);
+                if (e1 != cudaSuccess) { delete h; return set_err(FMB_ERR_CUDA, "occupancy query for the warp-specialised kernel", e1); }
+                if (occ_ws > 0) {
+                    const long long slots_ws = (long long) occ_ws * sms;
+                    h->plan_ws.grid = (int) (units < slots_ws ? units : slots_ws);
+                    if (units >= slots_ws) h->plan_ws.ctas_per_sm = occ_ws;
+                }
+            }
         }
     }
     h->phase = 0;
@@ -541,8 +563,10 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
         const char *ec = getenv("FMB_CHUNK"), *et = getenv("FMB_TAIL_PCT");
         const int chunk = ec ? atoi(ec) : FMB_DEFAULT_CHUNK;
         const bool forced = ec || et;
-        if (h->ctas_per_sm > 0 && chunk > 0 && chunk <= spb && spb % chunk == 0 &&
-            (forced || units >= 2LL * spb * h->grid)) {
+        for (fmb_handle::Plan *pl : {&h->plan, &h->plan_ws}) {
+            if (!(pl->ctas_per_sm > 0 && chunk > 0 && chunk <= spb && spb % chunk == 0 &&
+                  (forced || units >= 2LL * spb * pl->grid)))
+                continue;
             int tail_streams;
             if (et) {
                 int tail = atoi(et);
@@ -554,11 +578,11 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
                  * recompute).  1024 streams: 0.3475 -> 0.3337 ms per step (profiles/r02g_pdl_tail_sweep.txt) */
                 tail_streams = 0;
             } else {
-                tail_streams = (FMB_DEFAULT_TAIL_RUNS * chunk * h->grid + spb - 1) / spb;
+                tail_streams = (FMB_DEFAULT_TAIL_RUNS * chunk * pl->grid + spb - 1) / spb;
                 if (tail_streams > cfg->n_streams) tail_streams = cfg->n_streams;
             }
-            h->chunk = chunk;
-            h->n_whole = cfg->n_streams - tail_streams;
+            pl->chunk = chunk;
+            pl->n_whole = cfg->n_streams - tail_streams;
         }
     }
     {

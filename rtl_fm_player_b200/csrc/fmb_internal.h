@@ -78,6 +78,8 @@ typedef struct fmb_kparams {
     unsigned int seq;              /* this launch's sequence number                       */
     unsigned int *dev_err;         /* set to 1 if a flag wait ever times out (never hangs the GPU) */
     int pdl;                       /* 1: release the dependent launch at kernel start (griddepcontrol.launch_dependents) */
+    int ws;                        /* 1: launch the warp-specialised kernel of this configuration (fmb_demod_ws_occupancy > 0;
+                                      needs dec == 4 && dec_c0 == 0); `grid` is then that kernel's                          */
 } fmb_kparams;
 #define FMB_TICKET_SLOTS 4
 #define FMB_LR_BUFS 3              /* decoder-output buffers in rotation (see fmb_handle.d_lr)                  */
@@ -106,6 +108,7 @@ int fmb_launch_demod(const fmb_config *cfg, const fmb_kparams *p, const fmb_tabl
 int fmb_launch_deemph(const fmb_dparams *p, void *stream);
 /* resident CTAs per SM of the kernel this configuration selects */
 int fmb_demod_occupancy(const fmb_config *cfg, int *ctas_per_sm);
+int fmb_demod_ws_occupancy(const fmb_config *cfg, int *ctas_per_sm);
 /* 0 when (mode,size) has a compiled kernel. */
 int fmb_demod_supported(int mode, int size);
 

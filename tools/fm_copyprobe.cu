@@ -28,8 +28,14 @@ struct Dev {
 
 #define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, 256, "%s: %s", #call, cudaGetErrorString(e_)); rc = -1; goto done; } } while (0)
 
-extern "C" int fmprobe_copy(const int *devices, int n_dev, size_t bytes, int reps, int dir, int write_combined,
-                            double *gbs_h2d, double *gbs_d2h, double *seconds, char *err /* >= 256 bytes */)
+/* `sync` (may be NULL) is called after the buffers are set up and the warm-up copies are done, right before the
+ * timed copies start: a multi-process driver passes a barrier here so that all processes copy AT THE SAME TIME
+ * (allocating and touching 256 MiB of pinned memory takes far longer than copying it).  t_begin/t_end (may be NULL)
+ * receive the CLOCK_REALTIME seconds of the timed part, so that the driver can compute the aggregate rate over the
+ * union of the processes' intervals. */
+extern "C" int fmprobe_copy_sync(const int *devices, int n_dev, size_t bytes, int reps, int dir, int write_combined,
+                                 double *gbs_h2d, double *gbs_d2h, double *seconds, char *err /* >= 256 bytes */,
+                                 void (*sync)(void), double *t_begin, double *t_end)
 {
     std::vector<Dev> dv((size_t) n_dev);
     int rc = 0;
@@ -57,6 +63,8 @@ extern "C" int fmprobe_copy(const int *devices, int n_dev, size_t bytes, int rep
     for (int pass = 0; pass < 2; ++pass) {               /* pass 0: warm-up (2 copies), pass 1: timed */
         const int n = pass == 0 ? 2 : reps;
         for (int i = 0; i < n_dev; ++i) { CKP(cudaSetDevice(dv[(size_t) i].dev)); CKP(cudaDeviceSynchronize()); }
+        if (pass == 1 && sync) sync();
+        if (pass == 1 && t_begin) *t_begin = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
         const auto t0 = std::chrono::steady_clock::now();
         for (int r = 0; r < n; ++r)
             for (int i = 0; i < n_dev; ++i) {
@@ -67,6 +75,7 @@ extern "C" int fmprobe_copy(const int *devices, int n_dev, size_t bytes, int rep
             }
         for (int i = 0; i < n_dev; ++i) { CKP(cudaSetDevice(dv[(size_t) i].dev)); CKP(cudaDeviceSynchronize()); }
         dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (pass == 1 && t_end) *t_end = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
     }
     if (seconds) *seconds = dt;
     if (gbs_h2d) *gbs_h2d = do_in ? (double) bytes * reps * n_dev / dt * 1e-9 : 0.0;
@@ -82,4 +91,10 @@ done:
         if (d.s_out) cudaStreamDestroy(d.s_out);
     }
     return rc;
+}
+
+extern "C" int fmprobe_copy(const int *devices, int n_dev, size_t bytes, int reps, int dir, int write_combined,
+                            double *gbs_h2d, double *gbs_d2h, double *seconds, char *err)
+{
+    return fmprobe_copy_sync(devices, n_dev, bytes, reps, dir, write_combined, gbs_h2d, gbs_d2h, seconds, err, nullptr, nullptr, nullptr);
 }

@@ -31,14 +31,28 @@ def probe(devices, nbytes, reps, direction, wc):
 
 
 def _worker(dev, nbytes, reps, direction, wc, barrier, q):
+    """One process per device.  The barrier is passed INTO the probe and taken after its buffers are allocated,
+    touched and warmed up, right before the timed copies: all processes copy at the same time."""
     try:
-        probe([dev], nbytes, 2, direction, wc)          # context + first-touch outside the timed part
-        barrier.wait()
-        t0 = time.perf_counter()
-        a, b, s = probe([dev], nbytes, reps, direction, wc)
-        q.put((dev, a, b, s, t0))
+        lib = C.CDLL(os.path.join(ROOT, "tools", "libfmprobe.so"))
+        CB = C.CFUNCTYPE(None)
+        lib.fmprobe_copy_sync.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p,
+                                          CB, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        dv = (C.c_int * 1)(dev)
+        a, b, s, t0, t1 = (C.c_double() for _ in range(5))
+        err = C.create_string_buffer(256)
+        cb = CB(lambda: barrier.wait())
+        if lib.fmprobe_copy_sync(dv, 1, nbytes, reps, direction, wc, C.byref(a), C.byref(b), C.byref(s), err, cb,
+                                 C.byref(t0), C.byref(t1)) != 0:
+            raise RuntimeError(err.value.decode())
+        q.put((dev, t0.value, t1.value, None))
     except Exception as e:                               # noqa: BLE001
-        q.put((dev, 0.0, 0.0, -1.0, str(e)))
+        try:
+            barrier.abort()
+        except Exception:                                # noqa: BLE001
+            pass
+        q.put((dev, 0.0, 0.0, str(e)))
 
 
 def probe_processes(n, nbytes, reps, direction, wc):
@@ -50,10 +64,14 @@ def probe_processes(n, nbytes, reps, direction, wc):
     res = [q.get() for _ in ps]
     for p in ps:
         p.join()
-    if any(r[3] < 0 for r in res):
+    if any(r[3] for r in res):
         raise RuntimeError(str(res))
-    # the processes ran the same number of copies side by side: aggregate = sum of per-process rates
-    return sum(r[1] for r in res), sum(r[2] for r in res), max(r[3] for r in res)
+    # aggregate over the UNION of the processes' timed intervals (they start together behind the barrier)
+    span = max(r[2] for r in res) - min(r[1] for r in res)
+    overlap = min(r[2] for r in res) - max(r[1] for r in res)
+    in_b = nbytes if direction != 1 else 0
+    out_b = (nbytes // 16 if direction == 2 else nbytes) if direction != 0 else 0
+    return in_b * reps * n / span * 1e-9, out_b * reps * n / span * 1e-9, overlap / span
 
 
 def main():
@@ -67,7 +85,9 @@ def main():
     nbytes = args.mib << 20
     print(f"# raw copy ceiling: {args.reps} x {args.mib} MiB per device per direction, pinned host memory; "
           f"{ndev} visible GPUs, {os.cpu_count()} host cores; GB/s aggregate over the N devices")
-    print(f"{'N':>2} {'layout':>12} {'buffer':>6} {'H2D alone':>10} {'D2H alone':>10} {'mix H2D':>9} {'mix D2H':>8}")
+    print("# N processes: every process allocates and warms up its buffers, then all pass a barrier and copy together; rates are "
+          "over the union of their timed intervals (last column: fraction of that span during which ALL were copying)")
+    print(f"{'N':>2} {'layout':>12} {'buffer':>6} {'H2D alone':>10} {'D2H alone':>10} {'mix H2D':>9} {'mix D2H':>8} {'overlap':>8}")
     for n in [int(x) for x in args.gpus.split(",")]:
         if n > ndev:
             continue
@@ -80,7 +100,8 @@ def main():
                 h2d = f(0, wc)[0]
                 d2h = f(1, wc)[1]
                 mix = f(2, wc)
-                print(f"{n:>2} {layout:>12} {'wc' if wc else 'plain':>6} {h2d:>10.1f} {d2h:>10.1f} {mix[0]:>9.1f} {mix[1]:>8.1f}",
+                ov = f"{mix[2]:>8.2f}" if layout != "1 process" else f"{'-':>8}"
+                print(f"{n:>2} {layout:>12} {'wc' if wc else 'plain':>6} {h2d:>10.1f} {d2h:>10.1f} {mix[0]:>9.1f} {mix[1]:>8.1f} {ov}",
                       flush=True)
 
 
