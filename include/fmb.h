@@ -85,11 +85,12 @@ int fmb_default_config(fmb_config *cfg);
 int fmb_preset_stereo_192k(fmb_config *cfg);
 int fmb_preset_mono_192k(fmb_config *cfg);
 
-/* Tuning (read once here from the environment; results never depend on it): FMB_CHUNK = sub-tiles
- * (2048 demodulated samples) per fine-grain run of the demod kernel's dynamic work assignment, 0 = static
- * split, default 2; FMB_TAIL_PCT = percent of the streams handed out in such runs instead of whole
- * (default: about two such runs per CTA, for batches of at least two streams per CTA; smaller batches use
- * the static split).  See DESIGN.md "Kernel 1". */
+/* Tuning (read once here from the environment; results never depend on it): FMB_PDL=0 turns off the overlap of
+ * consecutive demod launches (programmatic dependent launch); FMB_WS=0 the warp-specialised mono kernel;
+ * FMB_CHUNK = sub-tiles (2048 demodulated samples) per fine-grain run of the demod kernel's dynamic work
+ * assignment, 0 = static split, default 2; FMB_TAIL_PCT = percent of the streams handed out in such runs
+ * instead of whole (default: none when launches overlap, else about two such runs per CTA; batches of fewer
+ * than two streams per CTA use the static split).  See DESIGN.md "Kernel 1". */
 int fmb_create(const fmb_config *cfg, fmb_handle **out);
 int fmb_destroy(fmb_handle *h);
 
@@ -135,6 +136,9 @@ int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, in
 int fmb_join(fmb_handle *h, void *stream);
 /* The handle's own compute stream (a cudaStream_t on cfg.device), for callers without one. */
 void *fmb_internal_stream(fmb_handle *h);
+/* Which demodulation kernel the NEXT process call launches ("fmb_demod_kernel", or "fmb_mono_ws_kernel": the
+ * warp-specialised kernel of the mono decoder on the 4:1 resampler path); for profiles and the benchmark. */
+const char *fmb_demod_kernel_name(const fmb_handle *h);
 /* Blocks until the handle's device has finished everything enqueued so far. */
 int fmb_sync(fmb_handle *h);
 

@@ -85,6 +85,7 @@ SIGNATURES = {
     "fmb_version": (C.c_char_p, []),
     "fmb_internal_stream": (C.c_void_p, [C.c_void_p]),
     "fmb_sync": (C.c_int, [C.c_void_p]),
+    "fmb_demod_kernel_name": (C.c_char_p, [C.c_void_p]),
     # include/fmb_multi.h: the C multi-GPU host (one worker thread per device)
     "fmb_multi_create": (C.c_int, [C.POINTER(FmbConfig), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "fmb_multi_destroy": (C.c_int, [C.c_void_p]),

@@ -94,6 +94,9 @@ class FmBatch:
     def next_out_count(self) -> int:
         return L.check(self._lib.fmb_next_out_count(self._h), "fmb_next_out_count")
 
+    def kernel_name(self) -> str:
+        return self._lib.fmb_demod_kernel_name(self._h).decode()
+
     def set_volume(self, volume: float) -> None:
         L.check(self._lib.fmb_set_volume(self._h, volume), "fmb_set_volume")
 

@@ -702,6 +702,15 @@ int fmb_join(fmb_handle *h, void *stream)
 
 void *fmb_internal_stream(fmb_handle *h) { return h ? (void *) h->s_main : nullptr; }
 
+const char *fmb_demod_kernel_name(const fmb_handle *h)
+{
+    if (!h) return "";
+    const fmb_config &c = h->cfg;
+    const bool dec4 = c.rate_out2 > 0 && h->fast % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0 &&
+                      h->fast / c.rate_out2 == 4 && h->phase / c.rate_out2 == 0;
+    return (h->plan_ws.grid > 0 && dec4) ? "fmb_mono_ws_kernel" : "fmb_demod_kernel";
+}
+
 int fmb_sync(fmb_handle *h)
 {
     if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
