@@ -386,3 +386,39 @@ def test_whole_stream_runs_on_random_bytes(monkeypatch):
     want = [PortOracle(**CONFIGS["stereo192"]).run(iq[s]) for s in range(uniq)]
     for s in range(n):
         assert np.array_equal(pcm[s], want[s % uniq]), s
+
+
+@pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("mono192", "fm_mono"), ("stereo240", "random"),
+                                          ("mono240", "fm_mono")])
+@pytest.mark.parametrize("pdl", ["1", "0"])
+def test_back_to_back_launches_of_a_full_batch_overlap_and_stay_exact(monkeypatch, cfgname, kind, pdl):
+    """1024 streams x 6 blocks enqueued back to back on one stream, no host synchronisation in between: consecutive
+    demod launches overlap at their ends (programmatic dependent launch; FMB_PDL=0: plain stream order), every stream
+    is handed out whole through the ticket counter, the carried state and the decoder-output buffers are ordered per
+    stream inside the kernels.  mono192 runs the warp-specialised kernel, stereo240 the in-place quirk, mono240 the
+    generic tick path.  16 distinct channels against the oracle, every replica identical to its original."""
+    import torch
+    monkeypatch.setenv("FMB_PDL", pdl)
+    n, uniq, blocks = 1024, 16, 6
+    c = CONFIGS[cfgname]
+    iq_u = np.stack([make_input(cfgname, kind, s, blocks) for s in range(uniq)])
+    d_u = torch.from_numpy(iq_u).cuda()
+    idx = torch.arange(n, device="cuda") % uniq
+    d_in = [d_u[:, b * B:(b + 1) * B].index_select(0, idx).contiguous() for b in range(blocks)]
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with R.FmBatch(cfg_for(cfgname, n_streams=n)) as fb:
+        pitch = (fb.max_out + 7) & ~7
+        d_out = torch.zeros((blocks, n, pitch), dtype=torch.int16, device="cuda")
+        counts = []
+        torch.cuda.synchronize()
+        for b in range(blocks):
+            counts.append(fb.next_out_count())
+            fb.process_device(d_in[b].data_ptr(), B, d_out[b].data_ptr(), pitch, st.cuda_stream)
+        fb.join(st.cuda_stream)
+        torch.cuda.synchronize()
+        fb.get_state(0, 1)                               # reports a device-side hand-over time-out, if any
+    got = np.concatenate([d_out[b, :, :counts[b]].cpu().numpy() for b in range(blocks)], axis=1)
+    for s in range(uniq):
+        assert np.array_equal(got[s], PortOracle(**c).run(iq_u[s])), s
+    assert np.array_equal(got.reshape(n // uniq, uniq, -1), np.broadcast_to(got[:uniq], (n // uniq, uniq, got.shape[1])))

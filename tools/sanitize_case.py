@@ -27,4 +27,27 @@ with R.FmBatch(R.DemodConfig(n_streams=n, **kw)) as fb:
 want = [PortOracle(**kw).run(iq[s]) for s in range(uniq)]
 for s in range(n):
     assert np.array_equal(pcm[s], want[s % uniq]), ("dynamic", s)
+# round 2: overlapping launches (programmatic dependent launch: per-stream hand-over counters, whole-stream tickets)
+# and the warp-specialised mono kernel (producer/consumer named barriers), device-resident back to back
+import torch
+del os.environ["FMB_CHUNK"], os.environ["FMB_TAIL_PCT"]
+for kw, kind, n in ((dict(rate_in=192000, rate_out2=48000, mode=2, size=90), "fm_stereo", 40),
+                    (dict(rate_in=192000, rate_out2=48000, mode=1, size=128), "fm_mono", 40)):
+    blocks, uniq = 3, 2
+    os.environ["FMB_CHUNK"], os.environ["FMB_TAIL_PCT"] = "8", "0"      # force the ticketed path on a small batch
+    iq = np.stack([R.synth.capture(kind, s % uniq, kw["rate_in"], 0, blocks * B // 2) for s in range(n)])
+    d_in = torch.from_numpy(iq).cuda()
+    with R.FmBatch(R.DemodConfig(n_streams=n, **kw)) as fb:
+        n_out = fb.next_out_count()
+        pitch = (n_out + 7) & ~7
+        d_out = torch.zeros((blocks, n, pitch), dtype=torch.int16, device="cuda")
+        st = torch.cuda.Stream()
+        for b in range(blocks):
+            fb.process_device(d_in.data_ptr() + b * B, iq.shape[1], d_out[b].data_ptr(), pitch, st.cuda_stream)
+        fb.join(st.cuda_stream)
+        torch.cuda.synchronize()
+    got = np.concatenate([d_out[b, :, :n_out].cpu().numpy() for b in range(blocks)], axis=1)
+    want = [PortOracle(**kw).run(iq[s]) for s in range(uniq)]
+    for s in range(n):
+        assert np.array_equal(got[s], want[s % uniq]), ("overlap", kw["mode"], s)
 print("sanitize case ok")
