@@ -235,6 +235,17 @@ def test_fmb_player_wav_files_equal_the_reference_pipeline(tmp_path, flag, cfgna
         want = tmp_path / f"ref{s}.wav"
         assert ref.ref_wav_write(str(want).encode(), CONFIGS[cfgname]["mode"], pcm.ctypes.data, pcm.size) == 0
         assert open(f + ".wav", "rb").read() == want.read_bytes(), f"channel {s}"
+    # the same channels sharded over several devices by the C multi-GPU host (-d: every visible GPU, or three shards
+    # sharing GPU 0 on a 1-GPU box): byte-identical WAV files again
+    ndev = R.device_count()
+    dlist = f"0-{ndev - 1}" if ndev >= 2 else "0,0,0"
+    for f in files:
+        os.rename(f + ".wav", f + ".single.wav")
+    r = subprocess.run([player, flag, "-w", "-d", dlist, *files], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"on {min(max(ndev, 3) if ndev < 2 else ndev, len(files))} device(s)" in r.stderr, r.stderr
+    for f in files:
+        assert open(f + ".wav", "rb").read() == open(f + ".single.wav", "rb").read(), f
     # raw PCM output keeps every sample (no cluster rule)
     r = subprocess.run([player, flag, files[0]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr

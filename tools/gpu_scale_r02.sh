@@ -4,7 +4,7 @@
 TAG=${1:-r02scale}; MAXN=${2:-8}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/${TAG}_gpus.txt; nproc >> gpurun_out/${TAG}_gpus.txt
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/${TAG}_pytest_multi.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_dropin.py -m gpu -q -k "multi or shard or fmb_player or device_resident or create_fails or uneven" > gpurun_out/${TAG}_pytest_multi.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_multi.log; tail -5 gpurun_out/${TAG}_pytest_multi.log
 timeout 900 python tools/h2d_ceiling.py --reps 10 > gpurun_out/${TAG}_h2d_ceiling.txt 2>&1; cat gpurun_out/${TAG}_h2d_ceiling.txt
 for N in 1 2 4 8; do
