@@ -245,6 +245,14 @@ int check_device_error(fmb_handle *h)
     return FMB_OK;
 }
 
+/* The warp-specialised kernel exists for the mono decoder on the 4:1 resampler path.  (A warp-specialised STEREO kernel
+ * -- front: 4 warps of channel FIR in two passes over the (A,B) halves, back: the 8 FIR warps -- was built, is
+ * bit-exact and ran at the same 0.336 ms per step as fmb_demod_kernel: tools/experiments/r02z_stereo_ws_kernel.patch.) */
+bool ws_kernel_applies(const fmb_handle *h, bool dec4)
+{
+    return h->plan_ws.grid > 0 && dec4 && h->cfg.mode == 1;
+}
+
 /* Enqueue one block-step: demod kernel on `sm`, de-emphasis kernel on the aux
  * stream.  d_iq/d_pcm are device pointers. */
 int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d_pcm, size_t pcm_pitch,
@@ -286,7 +294,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     /* which kernel: the warp-specialised one where this configuration has it and the resampler is on its 4:1 fast path */
     const bool dec4 = c.rate_out2 > 0 && h->fast % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0 &&
                       h->fast / c.rate_out2 == 4 && h->phase / c.rate_out2 == 0;
-    const bool ws = h->plan_ws.grid > 0 && dec4;
+    const bool ws = ws_kernel_applies(h, dec4);
     const fmb_handle::Plan &pl = ws ? h->plan_ws : h->plan;
     kp.ws = ws ? 1 : 0;
     kp.grid = pl.grid;
@@ -489,6 +497,12 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
                 delete h;
                 return set_err(FMB_ERR_CUDA, "occupancy query for the demod kernel", e1 != cudaSuccess ? e1 : e2);
             }
+            {
+                /* FMB_MAX_CTAS_PER_SM: run with fewer resident CTAs per SM than fit (diagnostic: how the step time
+                 * scales with the number of CTAs that share an SM) */
+                const char *em = getenv("FMB_MAX_CTAS_PER_SM");
+                if (em && atoi(em) > 0 && atoi(em) < occ) occ = atoi(em);
+            }
             const long long slots = (long long) occ * sms;
             h->plan.grid = (int) (units < slots ? units : slots);
             if (units >= slots) h->plan.ctas_per_sm = occ;
@@ -497,6 +511,10 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
             if (!(ew && atoi(ew) == 0) && cfg->rate_out2 > 0) {
                 e1 = (cudaError_t) fmb_demod_ws_occupancy(&kc, &occ_ws);
                 if (e1 != cudaSuccess) { delete h; return set_err(FMB_ERR_CUDA, "occupancy query for the warp-specialised kernel", e1); }
+                {
+                    const char *em = getenv("FMB_MAX_CTAS_PER_SM");
+                    if (em && atoi(em) > 0 && atoi(em) < occ_ws) occ_ws = atoi(em);
+                }
                 if (occ_ws > 0) {
                     const long long slots_ws = (long long) occ_ws * sms;
                     h->plan_ws.grid = (int) (units < slots_ws ? units : slots_ws);
@@ -708,7 +726,8 @@ const char *fmb_demod_kernel_name(const fmb_handle *h)
     const fmb_config &c = h->cfg;
     const bool dec4 = c.rate_out2 > 0 && h->fast % c.rate_out2 == 0 && h->phase % c.rate_out2 == 0 &&
                       h->fast / c.rate_out2 == 4 && h->phase / c.rate_out2 == 0;
-    return (h->plan_ws.grid > 0 && dec4) ? "fmb_mono_ws_kernel" : "fmb_demod_kernel";
+    if (!ws_kernel_applies(h, dec4)) return "fmb_demod_kernel";
+    return "fmb_mono_ws_kernel";
 }
 
 int fmb_sync(fmb_handle *h)
