@@ -123,6 +123,13 @@ int fmb_process(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t 
  * an internal stream so that it overlaps the next call's demodulation;
  * fmb_join() makes `stream` wait for everything enqueued so far.
  *
+ * Input readiness: consecutive demodulation launches of a handle OVERLAP at their ends (programmatic dependent
+ * launch), so a launch does not wait for the complete end of the KERNEL enqueued on `stream`
+ * immediately before it.  IQ that is already complete in device memory when the call is made, or is produced by
+ * copies / event waits on `stream` (cudaMemcpyAsync, cudaStreamWaitEvent: what fmb_submit does itself), needs
+ * nothing.  If a kernel of YOURS, enqueued on `stream` right before the call, produces the IQ, call
+ * fmb_input_ready(h) first: the next step is then launched in plain stream order behind everything on `stream`.
+ *
  * Threading: a handle is driven by ONE host thread at a time (like the reference's
  * demod_state, which only demod_thread_fn touches, :855-933); calls on one handle are
  * not re-entrant.  The caller MAY change `stream` between calls: the step then first
@@ -134,6 +141,9 @@ int fmb_process(fmb_handle *h, const uint8_t *iq_host, size_t iq_pitch, int16_t 
 int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, int16_t *pcm_dev, size_t pcm_pitch,
                        void *stream);
 int fmb_join(fmb_handle *h, void *stream);
+/* The next fmb_process_device() step waits for EVERYTHING enqueued on its stream before it, kernels included (see
+ * "Input readiness" above); costs that one step its overlap with the previous one. */
+int fmb_input_ready(fmb_handle *h);
 /* The handle's own compute stream (a cudaStream_t on cfg.device), for callers without one. */
 void *fmb_internal_stream(fmb_handle *h);
 /* Which demodulation kernel the NEXT process call launches ("fmb_demod_kernel", or "fmb_mono_ws_kernel": the

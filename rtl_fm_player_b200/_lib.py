@@ -64,6 +64,7 @@ SIGNATURES = {
     "fmb_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "fmb_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "fmb_join": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmb_input_ready": (C.c_int, [C.c_void_p]),
     "fmb_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "fmb_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "fmb_bind_thread_to_device_node": (C.c_int, [C.c_int]),

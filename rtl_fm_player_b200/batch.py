@@ -147,6 +147,10 @@ class FmBatch:
         L.check(self._lib.fmb_process_device(self._h, iq_ptr, iq_pitch, pcm_ptr, pcm_pitch, stream),
                 "fmb_process_device")
 
+    def input_ready(self) -> None:
+        """The next process_device() step waits for everything enqueued on its stream, kernels included."""
+        L.check(self._lib.fmb_input_ready(self._h), "fmb_input_ready")
+
     def join(self, stream: int = 0) -> None:
         L.check(self._lib.fmb_join(self._h, stream), "fmb_join")
 

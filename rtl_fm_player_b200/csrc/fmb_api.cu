@@ -104,6 +104,7 @@ struct fmb_handle {
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
     bool poisoned = false;           /* a CUDA call failed in the middle of a step: bookkeeping and device state disagree */
+    bool serial_next = false;        /* fmb_input_ready(): launch the next step in plain stream order */
     /* streams / events */
     cudaStream_t s_aux = nullptr, s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_demod[kLrBufs] = {}, ev_deemph[kLrBufs] = {};
@@ -323,7 +324,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     kp.de_done = h->d_de_done;
     kp.seq = h->seq;
     kp.dev_err = h->d_err;
-    kp.pdl = h->pdl;
+    kp.pdl = h->pdl && !h->serial_next;
 
     fmb_config kc = c;
     if (c.rate_out2 <= 0) kc.mode = 0;
@@ -373,6 +374,7 @@ int enqueue_step(fmb_handle *h, const uint8_t *d_iq, size_t iq_pitch, int16_t *d
     h->deemph_pending[b] = true;
     h->ticket_base[h->seq % FMB_TICKET_SLOTS] += ticket_step;
     h->seq++;
+    h->serial_next = false;
     h->last_stream = sm;
     h->have_last_stream = true;
 
@@ -708,6 +710,13 @@ int fmb_process_device(fmb_handle *h, const uint8_t *iq_dev, size_t iq_pitch, in
     if (!h || !iq_dev || !pcm_dev) return set_err(FMB_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(h->cfg.device));
     return enqueue_step(h, iq_dev, iq_pitch, pcm_dev, pcm_pitch, (cudaStream_t) stream, nullptr);
+}
+
+int fmb_input_ready(fmb_handle *h)
+{
+    if (!h) return set_err(FMB_ERR_ARG, "NULL handle");
+    h->serial_next = true;
+    return FMB_OK;
 }
 
 int fmb_join(fmb_handle *h, void *stream)

@@ -422,3 +422,30 @@ def test_back_to_back_launches_of_a_full_batch_overlap_and_stay_exact(monkeypatc
     for s in range(uniq):
         assert np.array_equal(got[s], PortOracle(**c).run(iq_u[s])), s
     assert np.array_equal(got.reshape(n // uniq, uniq, -1), np.broadcast_to(got[:uniq], (n // uniq, uniq, got.shape[1])))
+
+
+def test_iq_produced_by_a_kernel_on_the_same_stream_right_before_the_step():
+    """Consecutive demod launches overlap, so a launch does not wait for the complete end of a KERNEL enqueued on
+    its stream immediately before it (fmb.h, "Input readiness").  A caller whose own kernel produces the IQ says so
+    with fmb_input_ready(): here every block is copied into the input buffer by a device kernel on the same stream
+    right before the step, with no host synchronisation anywhere."""
+    import torch
+    n, uniq, blocks = 1024, 8, 5
+    iq_u = np.stack([make_input("stereo192", "fm_stereo", s, blocks) for s in range(uniq)])
+    d_u = torch.from_numpy(iq_u).cuda()
+    idx = torch.arange(n, device="cuda") % uniq
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with R.FmBatch(cfg_for("stereo192", n_streams=n)) as fb, torch.cuda.stream(st):
+        d_in = [torch.empty((n, B), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        d_out = torch.zeros((blocks, n, 8192), dtype=torch.int16, device="cuda")
+        for b in range(blocks):
+            torch.index_select(d_u[:, b * B:(b + 1) * B], 0, idx, out=d_in[b & 1])     # a kernel on `st` writes the IQ ...
+            fb.input_ready()                                                            # ... so say so
+            fb.process_device(d_in[b & 1].data_ptr(), B, d_out[b].data_ptr(), 8192, st.cuda_stream)
+        fb.join(st.cuda_stream)
+    torch.cuda.synchronize()
+    got = np.concatenate([d_out[b].cpu().numpy() for b in range(blocks)], axis=1)
+    for s in range(uniq):
+        assert np.array_equal(got[s], PortOracle(**CONFIGS["stereo192"]).run(iq_u[s])), s
+    assert np.array_equal(got.reshape(n // uniq, uniq, -1), np.broadcast_to(got[:uniq], (n // uniq, uniq, got.shape[1])))
