@@ -42,6 +42,6 @@ for v in vals:
         best = min(best, e0.elapsed_time(e1) / K)
     chk = int(pcm[:, :n_out].to(torch.int64).sum().item())
     if ref is None: ref = chk
-    print(f"{knob}={v:>8s} {mode}: {best:.4f} ms/step  checksum {'same' if chk == ref else 'DIFFERENT'}", flush=True)
+    print(f"{knob}={v:>8s} {mode}: {best:.4f} ms/step  checksum {chk} {"same" if chk == ref else "DIFFERENT"}", flush=True)
     fb.close() if hasattr(fb, "close") else None
     del fb

@@ -2,23 +2,9 @@
 // output (both components) cost a warp, with and without the discriminator, at 2 / 4 / 6 warps per scheduler?
 // Compare with the pipe bounds of the stage: FMA 47 packed x 2 = 94 cycles (+ 16 scalar with the discriminator),
 // ALU (32 PRMT + 8 LOP3) x 2 = 80 cycles (+ ~20 x 2 with the discriminator).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -prec-div=true -ftz=false -Iinclude -Irtl_fm_player_b200/csrc -o tools/ubench_chan tools/ubench_chan.cu rtl_fm_player_b200/csrc/build/fm_design.o
 #include "../rtl_fm_player_b200/csrc/fmb_kernels.cu"
 #include <cstdio>
-
-__device__ __forceinline__ float octant_finish(float y, float x, float z)     /* octant_angle without its division */
-{
-    const bool xn = x < 0.f, yn = y < 0.f;
-    const bool steep = fabsf(x) < fabsf(y);
-    const float t1 = add(0.2447f, fabsf(mul(0.0663f, z)));
-    const float u = add(fabsf(z), -1.f);
-    const float inner = add(K_PI_4, -mul(u, t1));
-    const float w = mul(z, inner);
-    const float base = steep ? K_PI_2 : K_PI;
-    const float sum = add(steep ? -w : w, yn ? -base : base);
-    float r = (steep || xn) ? sum : w;
-    if (y == 0.f && !xn) r = 0.f;
-    return r;
-}
 
 template <bool ROT, bool FMA, typename Emit>
 __device__ __forceinline__ void chan_fir_once(const unsigned rbase, const float *cs, const float2 one2, Emit emit)
