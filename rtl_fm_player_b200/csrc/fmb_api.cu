@@ -71,6 +71,7 @@ struct fmb_handle {
     };
     Plan plan;                 /* fmb_demod_kernel */
     Plan plan_ws;              /* the warp-specialised kernel of this configuration (grid 0: none) */
+    bool ws_generic = true;    /* ... also off the 4:1 fast path (env FMB_WS_GENERIC=0: A/B) */
     unsigned int *d_tickets = nullptr;         /* FMB_TICKET_SLOTS counters, used in rotation by launch sequence number */
     unsigned int ticket_base[FMB_TICKET_SLOTS] = {};
     /* overlap of consecutive demod launches (programmatic dependent launch, see fmb_kparams.done) */
@@ -251,7 +252,8 @@ int check_device_error(fmb_handle *h)
  * bit-exact and ran at the same 0.336 ms per step as fmb_demod_kernel: tools/experiments/r02z_stereo_ws_kernel.patch.) */
 bool ws_kernel_applies(const fmb_handle *h, bool dec4)
 {
-    return h->plan_ws.grid > 0 && dec4 && h->cfg.mode == 1;
+    /* mono: the 4:1 fast path and any other ratio on the kernel's generic tick path (FMB_WS_GENERIC=0: fast path only) */
+    return h->plan_ws.grid > 0 && (dec4 || h->ws_generic) && h->cfg.mode == 1 && h->cfg.rate_out2 > 0;
 }
 
 /* Enqueue one block-step: demod kernel on `sm`, de-emphasis kernel on the aux
@@ -510,6 +512,8 @@ int fmb_create(const fmb_config *cfg, fmb_handle **out)
             if (units >= slots) h->plan.ctas_per_sm = occ;
             /* FMB_WS=0: never use the warp-specialised kernels (tuning / A-B comparison) */
             const char *ew = getenv("FMB_WS");
+            const char *eg = getenv("FMB_WS_GENERIC");
+            h->ws_generic = !(eg && atoi(eg) == 0);
             if (!(ew && atoi(ew) == 0) && cfg->rate_out2 > 0) {
                 e1 = (cudaError_t) fmb_demod_ws_occupancy(&kc, &occ_ws);
                 if (e1 != cudaSuccess) { delete h; return set_err(FMB_ERR_CUDA, "occupancy query for the warp-specialised kernel", e1); }

@@ -79,7 +79,7 @@ typedef struct fmb_kparams {
     unsigned int *dev_err;         /* set to 1 if a flag wait ever times out (never hangs the GPU) */
     int pdl;                       /* 1: release the dependent launch at kernel start (griddepcontrol.launch_dependents) */
     int ws;                        /* 1: launch the warp-specialised kernel of this configuration (fmb_demod_ws_occupancy > 0;
-                                      needs dec == 4 && dec_c0 == 0); `grid` is then that kernel's                          */
+                                      mono; other ratios than dec == 4 && dec_c0 == 0 take its generic tick path); `grid` is then that kernel's */
 } fmb_kparams;
 #define FMB_TICKET_SLOTS 4
 #define FMB_LR_BUFS 3              /* decoder-output buffers in rotation (see fmb_handle.d_lr)                  */

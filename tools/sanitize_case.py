@@ -1,5 +1,6 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
-stereo 240 kHz (quirk path, ragged de-emphasis chunks), 5 streams x 3 blocks, plus mono and the drop-sample mode."""
+stereo 240 kHz (quirk path, ragged de-emphasis chunks), 5 streams x 3 blocks, plus mono (4:1 and generic tick path of the
+warp-specialised kernel) and the drop-sample mode."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,6 +10,7 @@ from oracle.oracle_py import PortOracle
 B = 262144
 for kw, kind in ((dict(rate_in=240000, rate_out2=48000, mode=2, size=90), "random"),
                  (dict(rate_in=192000, rate_out2=48000, mode=1, size=128), "fm_mono"),
+                 (dict(rate_in=240000, rate_out2=48000, mode=1, size=128), "fm_mono"),   # warp-specialised kernel, generic tick path
                  (dict(rate_in=192000, rate_out2=48000, mode=0, size=90), "fm_stereo")):
     n, blocks = 5, 3
     iq = np.stack([R.synth.capture(kind, s, kw["rate_in"], 0, blocks * B // 2) for s in range(n)])
@@ -32,7 +34,8 @@ for s in range(n):
 import torch
 del os.environ["FMB_CHUNK"], os.environ["FMB_TAIL_PCT"]
 for kw, kind, n in ((dict(rate_in=192000, rate_out2=48000, mode=2, size=90), "fm_stereo", 40),
-                    (dict(rate_in=192000, rate_out2=48000, mode=1, size=128), "fm_mono", 40)):
+                    (dict(rate_in=192000, rate_out2=48000, mode=1, size=128), "fm_mono", 40),
+                    (dict(rate_in=250000, rate_out2=44100, mode=1, size=90), "fm_mono", 40)):
     blocks, uniq = 3, 2
     os.environ["FMB_CHUNK"], os.environ["FMB_TAIL_PCT"] = "8", "0"      # force the ticketed path on a small batch
     iq = np.stack([R.synth.capture(kind, s % uniq, kw["rate_in"], 0, blocks * B // 2) for s in range(n)])
