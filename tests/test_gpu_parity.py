@@ -114,6 +114,26 @@ def test_time_segmentation_does_not_change_the_result(cfgname, kind, segs):
         assert np.array_equal(pcm[s], PortOracle(**CONFIGS[cfgname]).run(iq[s]))
 
 
+@pytest.mark.parametrize("cfgname", ["mono240", "mono240_32", "mono240_off"])
+def test_mono_off_the_4_to_1_path_runs_the_warp_specialised_kernel_and_equals_the_plain_one(monkeypatch, cfgname):
+    """Mono ratios other than 4:1 (the reference's default 240 kHz among them) take the generic tick path of
+    fmb_mono_ws_kernel; FMB_WS_GENERIC=0 sends them through fmb_demod_kernel.  Both against the oracle: a small batch
+    (static split over the CTAs: runs that start inside a stream, with lead-ins) and ticketed whole-stream runs."""
+    for n, blocks, ticketed in ((3, 3, False), (40, 2, True)):
+        if ticketed:
+            monkeypatch.setenv("FMB_CHUNK", "8"); monkeypatch.setenv("FMB_TAIL_PCT", "0")
+        uniq = min(n, 3)
+        iq = np.stack([make_input(cfgname, "fm_mono" if (s % uniq) % 2 else "random", s % uniq, blocks) for s in range(n)])
+        want = [PortOracle(**CONFIGS[cfgname]).run(iq[s]) for s in range(uniq)]
+        for generic, name in (("1", "fmb_mono_ws_kernel"), ("0", "fmb_demod_kernel")):
+            monkeypatch.setenv("FMB_WS_GENERIC", generic)
+            with R.FmBatch(cfg_for(cfgname, n_streams=n)) as fb:
+                assert fb.kernel_name() == name
+                pcm = fb.run(iq)
+            for s in range(n):
+                assert np.array_equal(pcm[s], want[s % uniq]), (cfgname, n, generic, s)
+
+
 @pytest.mark.parametrize("cfgname,kind", [("stereo192", "fm_stereo"), ("stereo192", "random"), ("mono192", "random"),
                                           ("stereo240", "fm_stereo"), ("stereo170_44", "fm_stereo"),
                                           ("stereo170_44", "random"), ("mono240_32", "fm_mono"), ("mono240", "random")])
