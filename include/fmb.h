@@ -86,7 +86,8 @@ int fmb_preset_stereo_192k(fmb_config *cfg);
 int fmb_preset_mono_192k(fmb_config *cfg);
 
 /* Tuning (read once here from the environment; results never depend on it): FMB_PDL=0 turns off the overlap of
- * consecutive demod launches (programmatic dependent launch); FMB_WS=0 the warp-specialised mono kernel;
+ * consecutive demod launches (programmatic dependent launch); FMB_WS=0 the warp-specialised mono kernel
+ * (FMB_WS_GENERIC=0: only off its 4:1 fast path, i.e. for the reference's default 240 kHz and other ratios);
  * FMB_CHUNK = sub-tiles (2048 demodulated samples) per fine-grain run of the demod kernel's dynamic work
  * assignment, 0 = static split, default 2; FMB_TAIL_PCT = percent of the streams handed out in such runs
  * instead of whole (default: none when launches overlap, else about two such runs per CTA; batches of fewer
@@ -147,7 +148,7 @@ int fmb_input_ready(fmb_handle *h);
 /* The handle's own compute stream (a cudaStream_t on cfg.device), for callers without one. */
 void *fmb_internal_stream(fmb_handle *h);
 /* Which demodulation kernel the NEXT process call launches ("fmb_demod_kernel", or "fmb_mono_ws_kernel": the
- * warp-specialised kernel of the mono decoder on the 4:1 resampler path); for profiles and the benchmark. */
+ * warp-specialised kernel of the mono decoder); for profiles and the benchmark. */
 const char *fmb_demod_kernel_name(const fmb_handle *h);
 /* Blocks until the handle's device has finished everything enqueued so far. */
 int fmb_sync(fmb_handle *h);
